@@ -1,0 +1,82 @@
+"""ctypes binding of libspmm_b200.so (C ABI declared in include/spmm_b200.h).
+
+There is no CPU fallback: if the library is missing, or a call returns non-zero, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspmm_b200.so")
+_lib = None
+
+vp, i32, i64, f32, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_ulonglong
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [("bias", vp), ("residual", vp), ("ld_residual", i32), ("pre_act", vp), ("ld_pre_act", i32),
+                ("dgelu_pre_act", vp), ("ld_dgelu_pre_act", i32), ("flags", i32), ("alpha", f32),
+                ("dropout_p", f32), ("dropout_seed", u64)]
+
+
+GEMM_OUT_F32, GEMM_ACCUMULATE, GEMM_GELU, GEMM_DGELU = 1, 2, 4, 8
+
+SIGNATURES = {
+    "spmm_version": (i32, []),
+    "spmm_gemm_bf16": (i32, [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, C.POINTER(GemmEpilogue), vp]),
+    "spmm_gemm_debug_config": (i32, [i32, i32, i32, i32]),
+    "spmm_attn_fwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, f32, f32, u64, vp]),
+    "spmm_attn_bwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32,
+                            i32, vp, i32, f32, f32, u64, vp]),
+    "spmm_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, f32, f32, u64, vp]),
+    "spmm_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, u64, f32, u64, vp]),
+    "spmm_embed_text_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "spmm_embed_text_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "spmm_pv_tokens_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "spmm_pv_tokens_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "spmm_embed_inputs_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    "spmm_embed_inputs_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    "spmm_colsum_bf16": (i32, [vp, i32, vp, i32, i32, vp]),
+    "spmm_cast_f32_to_bf16": (i32, [vp, vp, i64, vp]),
+    "spmm_add_bf16": (i32, [vp, vp, i64, vp]),
+    "spmm_dgelu_bf16": (i32, [vp, vp, vp, i64, vp]),
+    "spmm_gather_rows_bf16": (i32, [vp, vp, vp, i32, i64, vp]),
+    "spmm_scatter_add_rows_bf16": (i32, [vp, vp, vp, i32, i64, vp]),
+    "spmm_itc_fwd_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                               i64, vp]),
+    "spmm_itc_workspace_bytes": (i64, [i32, i32, i32]),
+    "spmm_sample_negatives": (i32, [vp, vp, i32, u64, u64, vp, vp, vp]),
+    "spmm_enqueue": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]),
+    "spmm_lm_loss_fwd_bwd": (i32, [vp, vp, i32, vp, i32, i32, i32, f32, vp, vp, vp, vp]),
+    "spmm_itm_loss_fwd_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "spmm_mpm_loss_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "spmm_ema_multi": (i32, [vp, vp, vp, vp, i64, f32, f32, vp]),
+    "spmm_grad_sumsq": (i32, [vp, i64, vp, vp]),
+    "spmm_adamw_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp, vp]),
+}
+
+
+class SpmmKernelError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the C-ABI library.  Fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SpmmKernelError("%s is missing: run `python -m spmm_b200.build` (or __graft_entry__.build()). "
+                                  "spmm_b200 has no CPU / PyTorch fallback." % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def call(name, *args):
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise SpmmKernelError("%s returned %d (%s)" % (name, rc, "argument/setup error" if rc < 0 else "cudaError"))
+    return rc

@@ -1,0 +1,278 @@
+// Flat-arena kernels: EMA of the momentum encoders, fp32->bf16 weight shadows, grad-norm, fused clip+AdamW,
+// and a few bandwidth-bound helpers.  All are HBM-roofline kernels: 128-bit accesses, grid = k * 148 CTAs.
+#include "common.cuh"
+#include "spmm_b200.h"
+
+namespace spmm {
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// p_m = p_m*m + p*(1-m): three separately rounded ops == reference SPMM_models.py:269 bit for bit.
+__global__ void __launch_bounds__(256) ema_kernel(const float4* __restrict__ p, float4* __restrict__ pm,
+                                                  uint2* __restrict__ p_bf, uint2* __restrict__ pm_bf, int64_t n4,
+                                                  float m, float om) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = ldg_stream(p + i);
+    float4 b = pm[i];
+    b.x = __fadd_rn(__fmul_rn(b.x, m), __fmul_rn(a.x, om));
+    b.y = __fadd_rn(__fmul_rn(b.y, m), __fmul_rn(a.y, om));
+    b.z = __fadd_rn(__fmul_rn(b.z, m), __fmul_rn(a.z, om));
+    b.w = __fadd_rn(__fmul_rn(b.w, m), __fmul_rn(a.w, om));
+    pm[i] = b;
+    if (p_bf) p_bf[i] = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+    if (pm_bf) pm_bf[i] = make_uint2(pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_kernel(const float4* __restrict__ s, uint2* __restrict__ d, int64_t n4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = ldg_stream(s + i);
+    d[i] = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ g, int64_t n4, float* out) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = ldg_stream(g + i);
+    acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.AdamW.step (decoupled decay).
+__global__ void __launch_bounds__(256)
+adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m1, float4* __restrict__ m2,
+             int64_t n4, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+             const float* __restrict__ sumsq, float max_norm, float gscale, const float* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0.f) return;
+  float coef = gscale;
+  if (sumsq != nullptr && max_norm > 0.f) {
+    const float total = sqrtf(*sumsq) * gscale;
+    const float c = max_norm / (total + 1e-6f);
+    coef *= fminf(c, 1.f);
+  }
+  const float step_size = lr / bc1;
+  const float decay = 1.f - lr * wd;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 w = p[i];
+    const float4 gr = ldg_stream(g + i);
+    float4 a = m1[i], v = m2[i];
+#define SPMM_ADAM1(c)                                           \
+  {                                                             \
+    const float gg = gr.c * coef;                               \
+    w.c *= decay;                                               \
+    a.c = a.c + (gg - a.c) * (1.f - b1);                        \
+    v.c = v.c * b2 + (1.f - b2) * gg * gg;                      \
+    const float denom = sqrtf(v.c) / bc2_sqrt + eps;            \
+    w.c -= step_size * (a.c / denom);                           \
+  }
+    SPMM_ADAM1(x) SPMM_ADAM1(y) SPMM_ADAM1(z) SPMM_ADAM1(w)
+#undef SPMM_ADAM1
+    p[i] = w; m1[i] = a; m2[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) add_bf16_kernel(uint4* __restrict__ d, const uint4* __restrict__ s, int64_t n8) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    uint4 a = d[i];
+    const uint4 b = s[i];
+    float x0, x1, y0, y1;
+#define SPMM_ADD2(c) unpack_bf16x2(a.c, x0, x1); unpack_bf16x2(b.c, y0, y1); a.c = pack_bf16x2(x0 + y0, x1 + y1);
+    SPMM_ADD2(x) SPMM_ADD2(y) SPMM_ADD2(z) SPMM_ADD2(w)
+#undef SPMM_ADD2
+    d[i] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) dgelu_kernel(const uint4* __restrict__ da, const uint4* __restrict__ pre,
+                                                    uint4* __restrict__ dp, int64_t n8) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const uint4 a = da[i], b = pre[i];
+    uint4 o;
+    float x0, x1, y0, y1;
+#define SPMM_DG2(c) unpack_bf16x2(a.c, x0, x1); unpack_bf16x2(b.c, y0, y1); o.c = pack_bf16x2(x0 * dgelu_erf(y0), x1 * dgelu_erf(y1));
+    SPMM_DG2(x) SPMM_DG2(y) SPMM_DG2(z) SPMM_DG2(w)
+#undef SPMM_DG2
+    dp[i] = o;
+  }
+}
+
+// out[c] += sum_r x[r][c]; block = 32x8 threads handles a 256-column x rows_per_block slab
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int ld, float* out, int rows,
+                                                     int cols, int rows_per_block) {
+  __shared__ float sh[8][33 * 8];
+  const int c0 = blockIdx.x * 256 + threadIdx.x % 32 * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < cols) {
+    for (int r = r0 + threadIdx.x / 32; r < r1; r += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (size_t)r * ld + c0);
+      float a, b;
+      unpack_bf16x2(u.x, a, b); acc[0] += a; acc[1] += b;
+      unpack_bf16x2(u.y, a, b); acc[2] += a; acc[3] += b;
+      unpack_bf16x2(u.z, a, b); acc[4] += a; acc[5] += b;
+      unpack_bf16x2(u.w, a, b); acc[6] += a; acc[7] += b;
+    }
+  }
+  const int w = threadIdx.x / 32, l = threadIdx.x % 32;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[w][l * 8 + j + l / 4] = acc[j];
+  __syncthreads();
+  if (w == 0 && c0 < cols) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+      for (int ww = 0; ww < 8; ++ww) s += sh[ww][l * 8 + j + l / 4];
+      if (c0 + j < cols) atomicAdd(out + c0 + j, s);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ idx,
+                                                          uint4* __restrict__ dst, int64_t row_vec) {
+  const int r = blockIdx.x;
+  const uint4* s = src + (int64_t)idx[r] * row_vec;
+  uint4* d = dst + (int64_t)r * row_vec;
+  for (int64_t i = threadIdx.x; i < row_vec; i += blockDim.x) d[i] = s[i];
+}
+
+// dst[idx[r]] += src[r]; duplicates in idx are legal (hard negatives may repeat) -> one CTA per DESTINATION row
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(uint4* __restrict__ dst, const int* __restrict__ idx,
+                                                               const uint4* __restrict__ src, int n_idx,
+                                                               int64_t row_vec) {
+  const int target = blockIdx.x;
+  for (int r = 0; r < n_idx; ++r) {
+    if (idx[r] != target) continue;
+    const uint4* s = src + (int64_t)r * row_vec;
+    uint4* d = dst + (int64_t)target * row_vec;
+    for (int64_t i = threadIdx.x; i < row_vec; i += blockDim.x) {
+      uint4 a = d[i];
+      const uint4 b = s[i];
+      float x0, x1, y0, y1;
+#define SPMM_ADD2(c) unpack_bf16x2(a.c, x0, x1); unpack_bf16x2(b.c, y0, y1); a.c = pack_bf16x2(x0 + y0, x1 + y1);
+      SPMM_ADD2(x) SPMM_ADD2(y) SPMM_ADD2(z) SPMM_ADD2(w)
+#undef SPMM_ADD2
+      d[i] = a;
+    }
+  }
+}
+
+static inline int flat_grid(int64_t n_items, int per_sm) {
+  int64_t blocks = (n_items + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * per_sm;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace spmm
+using namespace spmm;
+
+extern "C" int spmm_version(void) { return 100; }
+
+extern "C" int spmm_ema_multi(const float* p, float* p_m, void* p_bf16, void* p_m_bf16, int64_t n, float momentum,
+                              float one_minus_momentum, void* stream) {
+  SPMM_ARG(p && p_m && n >= 0 && n % 4 == 0);
+  SPMM_ARG(((uintptr_t)p & 15) == 0 && ((uintptr_t)p_m & 15) == 0 && ((uintptr_t)p_bf16 & 7) == 0 &&
+           ((uintptr_t)p_m_bf16 & 7) == 0);
+  if (n == 0) return 0;
+  ema_kernel<<<flat_grid(n / 4, 8), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)p, (float4*)p_m, (uint2*)p_bf16, (uint2*)p_m_bf16, n / 4, momentum, one_minus_momentum);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spmm_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  SPMM_ARG(src && dst && n >= 0 && n % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0);
+  if (n == 0) return 0;
+  cast_kernel<<<flat_grid(n / 4, 8), 256, 0, (cudaStream_t)stream>>>((const float4*)src, (uint2*)dst, n / 4);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spmm_grad_sumsq(const float* g, int64_t n, float* sumsq_out, void* stream) {
+  SPMM_ARG(g && sumsq_out && n >= 0 && n % 4 == 0 && ((uintptr_t)g & 15) == 0);
+  cudaError_t e = cudaMemsetAsync(sumsq_out, 0, sizeof(float), (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  if (n == 0) return 0;
+  sumsq_kernel<<<flat_grid(n / 4, 4), 256, 0, (cudaStream_t)stream>>>((const float4*)g, n / 4, sumsq_out);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spmm_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int step, const float* sumsq,
+                               float max_norm, float grad_scale, const float* skip_flag, void* stream) {
+  SPMM_ARG(p && g && exp_avg && exp_avg_sq && n >= 0 && n % 4 == 0 && step >= 1);
+  SPMM_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0);
+  if (n == 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adamw_kernel<<<flat_grid(n / 4, 8), 256, 0, (cudaStream_t)stream>>>(
+      (float4*)p, (const float4*)g, (float4*)exp_avg, (float4*)exp_avg_sq, n / 4, lr, beta1, beta2, eps, weight_decay,
+      (float)bc1, (float)sqrt(bc2), sumsq, max_norm, grad_scale, skip_flag);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spmm_add_bf16(void* dst, const void* src, int64_t n, void* stream) {
+  SPMM_ARG(dst && src && n >= 0 && n % 8 == 0 && (((uintptr_t)dst | (uintptr_t)src) & 15) == 0);
+  if (n == 0) return 0;
+  add_bf16_kernel<<<flat_grid(n / 8, 8), 256, 0, (cudaStream_t)stream>>>((uint4*)dst, (const uint4*)src, n / 8);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spmm_dgelu_bf16(const void* d_act, const void* pre_act, void* d_pre, int64_t n, void* stream) {
+  SPMM_ARG(d_act && pre_act && d_pre && n >= 0 && n % 8 == 0 &&
+           (((uintptr_t)d_act | (uintptr_t)pre_act | (uintptr_t)d_pre) & 15) == 0);
+  if (n == 0) return 0;
+  dgelu_kernel<<<flat_grid(n / 8, 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)d_act, (const uint4*)pre_act,
+                                                                      (uint4*)d_pre, n / 8);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spmm_colsum_bf16(const void* x, int ld, float* out, int rows, int cols, void* stream) {
+  SPMM_ARG(x && out && rows > 0 && cols > 0 && ld % 8 == 0 && cols % 8 == 0 && ((uintptr_t)x & 15) == 0);
+  const int col_blocks = (cols + 255) / 256;
+  int row_blocks = (2 * kNumSMs + col_blocks - 1) / col_blocks;
+  if (row_blocks > (rows + 31) / 32) row_blocks = (rows + 31) / 32;
+  if (row_blocks < 1) row_blocks = 1;
+  const int rpb = (rows + row_blocks - 1) / row_blocks;
+  colsum_kernel<<<dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, out, rows,
+                                                                                cols, rpb);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spmm_gather_rows_bf16(const void* src, const int* idx, void* dst, int n_idx, int64_t row_elems,
+                                     void* stream) {
+  SPMM_ARG(src && idx && dst && n_idx > 0 && row_elems % 8 == 0 && (((uintptr_t)dst | (uintptr_t)src) & 15) == 0);
+  gather_rows_kernel<<<n_idx, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, idx, (uint4*)dst, row_elems / 8);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spmm_scatter_add_rows_bf16(void* dst, const int* idx, const void* src, int n_idx, int64_t row_elems,
+                                          void* stream) {
+  SPMM_ARG(src && idx && dst && n_idx > 0 && row_elems % 8 == 0 && (((uintptr_t)dst | (uintptr_t)src) & 15) == 0);
+  // destination rows are indexed 0..n_idx-1 (the in-batch gather of SPMM_models.py:165-178 is a map batch -> batch)
+  scatter_add_rows_kernel<<<n_idx, 256, 0, (cudaStream_t)stream>>>((uint4*)dst, idx, (const uint4*)src, n_idx,
+                                                                   row_elems / 8);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,438 @@
+// bf16 GEMM on 5th-gen tensor cores (sm_100a): TMA -> swizzled smem -> tcgen05.mma -> TMEM -> fused epilogue.
+//
+//   C[M,N] (+)= epilogue( alpha * A[M,K] . B[N,K]^T )
+//
+// Replaces every nn.Linear on the hot path (reference xbert.py:280-298 Q/K/V, :370 attn-out, :435 FFN-up,
+// :448 FFN-down, :673/:695 LM head; SPMM_models.py:92,95 projections) and their autograd dgrad/wgrad.
+// Operands may be K-major (row-major [rows][K]) or MN-major (row-major [K][rows]) so that
+// fwd (X.W^T), dgrad (dY.W) and wgrad (dY^T.X) all run without a transpose pass.
+//
+// Structure: persistent CTAs (one per SM), 256 threads:
+//   warp 0 lane 0 : TMA producer      (smem full/empty ring, kStages deep)
+//   warp 1 lane 0 : tcgen05.mma issuer (accumulators double-buffered in TMEM: 2 x BN columns)
+//   warp 2        : TMEM alloc/dealloc
+//   warps 4..7    : epilogue (tcgen05.ld -> bias / GELU / dGELU / dropout / residual -> global)
+#include <cuda.h>
+#include <mutex>
+
+#include "common.cuh"
+#include "spmm_b200.h"
+
+namespace spmm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct GemmParams {
+  int M, N, K;
+  int a_mn, b_mn;  // operand majors: 0 = K-major, 1 = MN-major
+  void* C;
+  int ldc;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  int ldr;
+  __nv_bfloat16* pre;
+  int ldp;
+  const __nv_bfloat16* aux;
+  int ldaux;
+  int flags;
+  float alpha;
+  unsigned long long drop_seed;
+  uint32_t drop_thresh16;  // keep iff 16-bit draw >= thresh
+  float drop_inv_keep;
+  uint32_t mn_lbo, mn_sbo;  // MN-major descriptor strides (bytes)
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ bool drop_keep16(unsigned long long seed, unsigned long long e, uint32_t thresh16) {
+  const uint32_t h = hash_u32(seed, e >> 1);
+  return ((h >> (16 * (e & 1))) & 0xFFFFu) >= thresh16;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % num_m) * BM, n0 = (tile / num_m) * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        if (p.a_mn == 0) {
+          tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &map_a, &full_bar[stage], m0 + c * 64, kb * BK);
+        }
+        if (p.b_mn == 0) {
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &map_b, &full_bar[stage], n0 + c * 64, kb * BK);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t adesc = p.a_mn ? umma_smem_desc(sa + k * 2048, p.mn_lbo, p.mn_sbo)
+                                        : umma_smem_desc(sa + k * 32, 16, 1024);
+          const uint64_t bdesc = p.b_mn ? umma_smem_desc(sb + k * 2048, p.mn_lbo, p.mn_sbo)
+                                        : umma_smem_desc(sb + k * 32, 16, 1024);
+          tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+        }
+        tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool out_f32 = p.flags & SPMM_GEMM_OUT_F32, accum = p.flags & SPMM_GEMM_ACCUMULATE;
+    const bool do_gelu = p.flags & SPMM_GEMM_GELU, do_dgelu = p.flags & SPMM_GEMM_DGELU;
+    const bool do_drop = p.drop_thresh16 != 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % num_m) * BM, n0 = (tile / num_m) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const __nv_bfloat16* side = do_dgelu ? p.aux : p.residual;  // at most one bf16 side input per call
+      const int lds = do_dgelu ? p.ldaux : p.ldr;
+      uint4 side_next[4];
+      auto load_side = [&](int c, uint4(&dst)[4]) {
+        const int col0 = n0 + c * 32;
+        if (side != nullptr && row_ok && col0 + 32 <= p.N) {
+          const uint4* sp = reinterpret_cast<const uint4*>(side + (size_t)row * lds + col0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = __ldg(sp + i);
+        }
+      };
+      load_side(0, side_next);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint4 side_cur[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) side_cur[i] = side_next[i];
+        if (c + 1 < BN / 32) load_side(c + 1, side_next);
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        const bool full_chunk = col0 + 32 <= p.N;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        if (p.bias != nullptr) {
+          if (full_chunk) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(bp + i);
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
+        }
+        if (p.pre != nullptr) {
+          __nv_bfloat16* pp = p.pre + (size_t)row * p.ldp + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+              o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              reinterpret_cast<uint4*>(pp)[i] = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) pp[j] = f2bf(v[j]);
+          }
+        }
+        if (do_gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (do_drop) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const unsigned long long e = (unsigned long long)row * (unsigned long long)p.N + (col0 + j);
+            v[j] = drop_keep16(p.drop_seed, e, p.drop_thresh16) ? v[j] * p.drop_inv_keep : 0.f;
+          }
+        }
+        if (side != nullptr) {
+          float s[32];
+          if (full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              unpack_bf16x2(side_cur[i].x, s[8 * i], s[8 * i + 1]); unpack_bf16x2(side_cur[i].y, s[8 * i + 2], s[8 * i + 3]);
+              unpack_bf16x2(side_cur[i].z, s[8 * i + 4], s[8 * i + 5]); unpack_bf16x2(side_cur[i].w, s[8 * i + 6], s[8 * i + 7]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s[j] = (col0 + j < p.N) ? bf2f(side[(size_t)row * lds + col0 + j]) : 0.f;
+          }
+          if (do_dgelu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= dgelu_erf(s[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += s[j];
+          }
+        }
+        if (out_f32) {
+          float* cp = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              if (accum) {
+                const float4 old = reinterpret_cast<float4*>(cp)[i];
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              reinterpret_cast<float4*>(cp)[i] = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) cp[j] = accum ? cp[j] + v[j] : v[j];
+          }
+        } else {
+          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+              o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              reinterpret_cast<uint4*>(cp)[i] = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) cp[j] = f2bf(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows with leading dimension `ld` elements.
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                    uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -2;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -3;
+}
+
+static uint32_t g_mn_lbo = 8192, g_mn_sbo = 1024;
+static int g_force_bn = 0;
+static int g_max_ctas = 0;
+
+template <int BN>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  int ctas = tiles < kNumSMs ? tiles : kNumSMs;
+  if (g_max_ctas > 0 && ctas > g_max_ctas) ctas = g_max_ctas;
+  gemm_bf16_kernel<BN><<<ctas, 256, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+static int pick_bn(int M, int N) {
+  if (g_force_bn) return g_force_bn;
+  if (N <= 128) return 128;
+  const int nm = (M + BM - 1) / BM;
+  auto cost = [&](int bn) {
+    const long tiles = (long)nm * ((N + bn - 1) / bn);
+    const long waves = (tiles + kNumSMs - 1) / kNumSMs;
+    return waves * (bn + 24);  // per-tile time ~ BN plus a fixed prologue/epilogue share
+  };
+  return cost(256) <= cost(128) ? 256 : 128;
+}
+
+}  // namespace spmm
+
+using namespace spmm;
+
+extern "C" int spmm_gemm_debug_config(int mn_lbo_bytes, int mn_sbo_bytes, int force_bn, int max_ctas) {
+  if (mn_lbo_bytes > 0) g_mn_lbo = mn_lbo_bytes;
+  if (mn_sbo_bytes > 0) g_mn_sbo = mn_sbo_bytes;
+  g_force_bn = force_bn;
+  g_max_ctas = max_ctas;
+  return 0;
+}
+
+extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major,
+                              void* C, int ldc, int M, int N, int K, const spmm_gemm_epilogue* epi, void* stream) {
+  SPMM_ARG(A && B && C && M > 0 && N > 0 && K > 0);
+  SPMM_ARG(lda % 8 == 0 && ldb % 8 == 0);
+  SPMM_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = a_mn_major ? 1 : 0;
+  p.b_mn = b_mn_major ? 1 : 0;
+  p.C = C; p.ldc = ldc;
+  p.alpha = 1.f;
+  p.mn_lbo = g_mn_lbo; p.mn_sbo = g_mn_sbo;
+  if (epi) {
+    p.bias = epi->bias;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(epi->residual); p.ldr = epi->ld_residual;
+    p.pre = reinterpret_cast<__nv_bfloat16*>(epi->pre_act); p.ldp = epi->ld_pre_act;
+    p.aux = reinterpret_cast<const __nv_bfloat16*>(epi->dgelu_pre_act); p.ldaux = epi->ld_dgelu_pre_act;
+    p.flags = epi->flags;
+    p.alpha = epi->alpha;
+    if (epi->dropout_p > 0.f) {
+      p.drop_seed = epi->dropout_seed;
+      p.drop_thresh16 = (uint32_t)(epi->dropout_p * 65536.f + 0.5f);
+      p.drop_inv_keep = 1.f / (1.f - epi->dropout_p);
+    }
+  }
+  const bool out_f32 = p.flags & SPMM_GEMM_OUT_F32;
+  SPMM_ARG(ldc % (out_f32 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  SPMM_ARG(!((p.flags & SPMM_GEMM_ACCUMULATE) && !out_f32));
+  SPMM_ARG(!((p.flags & SPMM_GEMM_DGELU) && (p.residual || !p.aux)));
+  SPMM_ARG(!p.residual || p.ldr % 8 == 0);
+  SPMM_ARG(!p.aux || p.ldaux % 8 == 0);
+  SPMM_ARG(!p.pre || p.ldp % 8 == 0);
+  SPMM_ARG(!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+
+  const int bn = pick_bn(M, N);
+  CUtensorMap ma, mb;
+  int rc;
+  if (!p.a_mn) rc = make_map(&ma, A, K, M, lda, BK, BM);
+  else rc = make_map(&ma, A, M, K, lda, 64, BK);
+  if (rc) return rc;
+  if (!p.b_mn) rc = make_map(&mb, B, K, N, ldb, BK, bn);
+  else rc = make_map(&mb, B, N, K, ldb, 64, BK);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return bn == 256 ? launch<256>(ma, mb, p, st) : launch<128>(ma, mb, p, st);
+}

@@ -1,0 +1,251 @@
+// Fused loss heads (forward + gradient in one pass, fp32 math over bf16 activations):
+//   LM  : next-token CE over ALL positions + momentum-distillation soft CE (reference SPMM_models.py:233-238)
+//   ITM : Linear(2H,2) + CE with labels [1]*B + [0]*2B                      (SPMM_models.py:201-206)
+//   MPM : Linear(H,1) + masked MSE, x5                                      (SPMM_models.py:251-256)
+#include "common.cuh"
+#include "spmm_b200.h"
+
+namespace spmm {
+
+// ------------------------------------------------------------------ LM loss
+__global__ void lm_count_kernel(const int64_t* __restrict__ ids, int B, int L, float* ws) {
+  __shared__ float sh[32];
+  float c = 0.f;
+  for (int i = threadIdx.x; i < B * (L - 1); i += blockDim.x) {
+    const int b = i / (L - 1), t = i % (L - 1);
+    c += (ids[(size_t)b * L + t + 1] != 0) ? 1.f : 0.f;   // labels != 0, SPMM_models.py:237
+  }
+  c = block_sum(c, sh);
+  if (threadIdx.x == 0) { ws[0] = c; ws[1] = 0.f; ws[2] = 0.f; }
+}
+
+constexpr int LM_MAXV = 320;  // per-lane register budget: 10 logits
+
+__global__ void __launch_bounds__(256)
+lm_loss_kernel(const __nv_bfloat16* __restrict__ logits, const __nv_bfloat16* __restrict__ teacher, int ld,
+               const int64_t* __restrict__ ids, int B, int L, int V, float alpha, float* ws,
+               __nv_bfloat16* __restrict__ dlogits) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B * L) return;
+  const int b = row / L, t = row % L;
+  __nv_bfloat16* drow = dlogits + (size_t)row * ld;
+  if (t == L - 1) {  // sliced away by [:, :-1] -> zero gradient
+    for (int c = lane; c < ld; c += 32) drow[c] = f2bf(0.f);
+    return;
+  }
+  const int64_t label = ids[(size_t)b * L + t + 1];
+  const float n_valid = ws[0];
+  float s[LM_MAXV / 32], m[LM_MAXV / 32];
+  float mxs = -INFINITY, mxm = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < LM_MAXV / 32; ++i) {
+    const int c = lane + 32 * i;
+    s[i] = c < V ? bf2f(logits[(size_t)row * ld + c]) : -INFINITY;
+    m[i] = c < V ? bf2f(teacher[(size_t)row * ld + c]) : -INFINITY;
+    mxs = fmaxf(mxs, s[i]);
+    mxm = fmaxf(mxm, m[i]);
+  }
+  mxs = warp_max(mxs);
+  mxm = warp_max(mxm);
+  float ses = 0.f, sem = 0.f, dot = 0.f, slab = 0.f;
+#pragma unroll
+  for (int i = 0; i < LM_MAXV / 32; ++i) {
+    const int c = lane + 32 * i;
+    if (c < V) {
+      const float es = __expf(s[i] - mxs), em = __expf(m[i] - mxm);
+      ses += es; sem += em; dot += em * s[i];
+      if (c == label) slab = s[i];
+      s[i] = es; m[i] = em;
+    }
+  }
+  ses = warp_sum(ses); sem = warp_sum(sem); dot = warp_sum(dot); slab = warp_sum(slab);
+  const float lse = mxs + __logf(ses);
+  const float ce = lse - slab;
+  const bool valid = label != 0;
+  const float distill = lse - dot / sem;
+  if (lane == 0) {
+    atomicAdd(ws + 1, ce);
+    if (valid) atomicAdd(ws + 2, distill);
+  }
+  const float w_ce = (1.f - alpha) / (float)(B * (L - 1));
+  const float w_ds = valid ? alpha / n_valid : 0.f;
+#pragma unroll
+  for (int i = 0; i < LM_MAXV / 32; ++i) {
+    const int c = lane + 32 * i;
+    if (c < V) {
+      const float ps = s[i] / ses, pm = m[i] / sem;
+      const float g = w_ce * (ps - (c == label ? 1.f : 0.f)) + w_ds * (ps - pm);
+      drow[c] = f2bf(g);
+    } else if (c < ld) {
+      drow[c] = f2bf(0.f);
+    }
+  }
+}
+
+__global__ void lm_final_kernel(const float* ws, int B, int L, float alpha, float* loss) {
+  *loss = (1.f - alpha) * ws[1] / (float)(B * (L - 1)) + alpha * ws[2] / ws[0];
+}
+
+// ------------------------------------------------------------------ ITM head + CE (single CTA; ~1 MFLOP)
+__global__ void __launch_bounds__(1024)
+itm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int n_rows,
+           int n_pos, int D, float* loss, __nv_bfloat16* __restrict__ dx, float* dw, float* db) {
+  extern __shared__ float sdl[];  // [n_rows][2] dlogits
+  __shared__ float sh[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float lsum = 0.f;
+  for (int r = warp; r < n_rows; r += nw) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int k = lane; k < D; k += 32) {
+      const float xv = bf2f(x[(size_t)r * D + k]);
+      a0 += xv * w[k];
+      a1 += xv * w[D + k];
+    }
+    a0 = warp_sum(a0) + bias[0];
+    a1 = warp_sum(a1) + bias[1];
+    const float mx = fmaxf(a0, a1);
+    const float e0 = __expf(a0 - mx), e1 = __expf(a1 - mx), se = e0 + e1;
+    const int label = r < n_pos ? 1 : 0;
+    if (lane == 0) {
+      lsum += mx + __logf(se) - (label ? a1 : a0);
+      sdl[2 * r + 0] = (e0 / se - (label == 0 ? 1.f : 0.f)) / n_rows;
+      sdl[2 * r + 1] = (e1 / se - (label == 1 ? 1.f : 0.f)) / n_rows;
+    }
+  }
+  lsum = block_sum(lsum, sh);  // contains the __syncthreads that publishes sdl
+  if (threadIdx.x == 0) *loss = lsum / n_rows;
+  for (int k = threadIdx.x; k < D; k += blockDim.x) {
+    float g0 = 0.f, g1 = 0.f;
+    for (int r = 0; r < n_rows; ++r) {
+      const float xv = bf2f(x[(size_t)r * D + k]);
+      g0 += sdl[2 * r] * xv;
+      g1 += sdl[2 * r + 1] * xv;
+    }
+    dw[k] += g0;
+    dw[D + k] += g1;
+  }
+  if (threadIdx.x < 2) {
+    float g = 0.f;
+    for (int r = 0; r < n_rows; ++r) g += sdl[2 * r + threadIdx.x];
+    db[threadIdx.x] += g;
+  }
+  for (int i = threadIdx.x; i < n_rows * D; i += blockDim.x) {
+    const int r = i / D, k = i % D;
+    dx[i] = f2bf(sdl[2 * r] * w[k] + sdl[2 * r + 1] * w[D + k]);
+  }
+}
+
+// ------------------------------------------------------------------ MPM tail
+__global__ void mpm_count_kernel(const float* __restrict__ mpm, int n, float* ws) {
+  __shared__ float sh[32];
+  float c = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += (mpm[i] == 0.f) ? 1.f : 0.f;  // (1 - mpm_mask).bool()
+  c = block_sum(c, sh);
+  if (threadIdx.x == 0) { ws[0] = c; ws[1] = 0.f; }
+}
+
+// rows r = b*(n_prop+1) + j; only j < n_prop with mpm_mask == 0 contribute
+__global__ void __launch_bounds__(256)
+mpm_kernel(const __nv_bfloat16* __restrict__ t, const float* __restrict__ w, const float* __restrict__ bias,
+           const float* __restrict__ pv, const float* __restrict__ mpm, int batch, int n_prop, int H, float* ws,
+           __nv_bfloat16* __restrict__ dt, float* dw, float* db) {
+  extern __shared__ float shw[];  // [8][H]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = batch * (n_prop + 1);
+  const float n_valid = ws[0];
+  float pw[32];  // per-lane partial dw for columns lane + 32*i  (H <= 1024)
+#pragma unroll
+  for (int i = 0; i < 32; ++i) pw[i] = 0.f;
+  float pb = 0.f, pl = 0.f;
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+    const int b = r / (n_prop + 1), j = r % (n_prop + 1);
+    const bool valid = j < n_prop && mpm[b * n_prop + j] == 0.f;
+    float dpred = 0.f;
+    if (valid) {
+      float a = 0.f;
+      for (int k = lane; k < H; k += 32) a += bf2f(t[(size_t)r * H + k]) * w[k];
+      a = warp_sum(a) + bias[0];
+      const float diff = a - pv[b * n_prop + j];
+      pl += diff * diff;                       // identical in every lane
+      dpred = 5.f * 2.f * diff / n_valid;      // d(5 * mse)/d pred
+      pb += dpred;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int k = lane + 32 * i;
+      if (k < H) {
+        if (valid) pw[i] += dpred * bf2f(t[(size_t)r * H + k]);
+        dt[(size_t)r * H + k] = f2bf(dpred * w[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int k = lane + 32 * i;
+    if (k < H) shw[warp * H + k] = pw[i];
+  }
+  __shared__ float sb[8], sl[8];
+  if (lane == 0) { sb[warp] = pb; sl[warp] = pl; }
+  __syncthreads();
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) s += shw[ww * H + k];
+    atomicAdd(dw + k, s);
+  }
+  if (threadIdx.x == 0) {
+    float s = 0.f, l = 0.f;
+    for (int ww = 0; ww < 8; ++ww) { s += sb[ww]; l += sl[ww]; }
+    atomicAdd(db, s);
+    atomicAdd(ws + 1, l);
+  }
+}
+
+__global__ void mpm_final_kernel(const float* ws, float* loss) { *loss = 5.f * ws[1] / ws[0]; }
+
+}  // namespace spmm
+using namespace spmm;
+
+extern "C" int spmm_lm_loss_fwd_bwd(const void* logits, const void* teacher_logits, int ld, const int64_t* ids, int B,
+                                    int L, int V, float alpha, float* loss, void* dlogits, float* workspace,
+                                    void* stream) {
+  SPMM_ARG(logits && teacher_logits && ids && loss && dlogits && workspace && B > 0 && L > 1 && V > 0 && V <= LM_MAXV &&
+           ld >= V);
+  cudaStream_t st = (cudaStream_t)stream;
+  lm_count_kernel<<<1, 256, 0, st>>>(ids, B, L, workspace);
+  SPMM_CHECK_LAUNCH();
+  lm_loss_kernel<<<(B * L + 7) / 8, 256, 0, st>>>((const __nv_bfloat16*)logits, (const __nv_bfloat16*)teacher_logits, ld,
+                                                  ids, B, L, V, alpha, workspace, (__nv_bfloat16*)dlogits);
+  SPMM_CHECK_LAUNCH();
+  lm_final_kernel<<<1, 1, 0, st>>>(workspace, B, L, alpha, loss);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spmm_itm_loss_fwd_bwd(const void* x, const float* w, const float* b, int n_rows, int n_pos, int D,
+                                     float* loss, void* dx, float* dw, float* db, void* stream) {
+  SPMM_ARG(x && w && b && loss && dx && dw && db && n_rows > 0 && D > 0 && n_rows <= 4096);
+  itm_kernel<<<1, 1024, (size_t)n_rows * 2 * sizeof(float), (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, w, b, n_rows, n_pos, D, loss, (__nv_bfloat16*)dx, dw, db);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spmm_mpm_loss_fwd_bwd(const void* t, const float* w, const float* b, const float* pv,
+                                     const float* mpm_mask, int batch, int n_prop, int H, float* loss, void* dt,
+                                     float* dw, float* db, float* workspace, void* stream) {
+  SPMM_ARG(t && w && b && pv && mpm_mask && loss && dt && dw && db && workspace && batch > 0 && n_prop > 0 && H > 0 &&
+           H <= 1024);
+  cudaStream_t st = (cudaStream_t)stream;
+  mpm_count_kernel<<<1, 256, 0, st>>>(mpm_mask, batch * n_prop, workspace);
+  SPMM_CHECK_LAUNCH();
+  const int rows = batch * (n_prop + 1);
+  int grid = (rows + 7) / 8;
+  if (grid > kNumSMs) grid = kNumSMs;
+  mpm_kernel<<<grid, 256, (size_t)8 * H * sizeof(float), st>>>((const __nv_bfloat16*)t, w, b, pv, mpm_mask, batch, n_prop,
+                                                               H, workspace, (__nv_bfloat16*)dt, dw, db);
+  SPMM_CHECK_LAUNCH();
+  mpm_final_kernel<<<1, 1, 0, st>>>(workspace, loss);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,388 @@
+"""Per-kernel parity tests: every C-ABI entry point against a plain PyTorch fp32 restatement
+(or the oracle) on seeded inputs.  Run on the GPU box: pytest -m gpu."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from spmm_b200 import kernels as K
+
+DEV = "cuda"
+BF = torch.bfloat16
+
+
+def rnd(*shape, scale=1.0, seed=0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+# ---------------------------------------------------------------- arena kernels
+def test_ema_bit_exact():
+    n = 1 << 20
+    p, pm = rnd(n, seed=1), rnd(n, seed=2)
+    ref = pm * 0.995 + p * (1. - 0.995)              # the reference expression, SPMM_models.py:269
+    pb, pmb = torch.empty(n, device=DEV, dtype=BF), torch.empty(n, device=DEV, dtype=BF)
+    K.ema(p, pm, pb, pmb, 0.995)
+    assert torch.equal(pm, ref)
+    assert torch.equal(pb, p.to(BF)) and torch.equal(pmb, ref.to(BF))
+
+
+def test_adamw_matches_torch():
+    n = 4096 * 8
+    p0, g = rnd(n, seed=3), rnd(n, seed=4, scale=3.0)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=5e-5, weight_decay=0.02)
+    p, m1, m2 = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    ss = torch.zeros(1, device=DEV)
+    for step in range(1, 4):
+        ref_p.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 5.0)
+        opt.step()
+        K.grad_sumsq(g, ss)
+        assert abs(float(ss) - float(g.double().pow(2).sum())) < 1e-3 * float(ss)
+        K.adamw(p, g, m1, m2, 5e-5, 0.9, 0.999, 1e-8, 0.02, step, sumsq=ss, max_norm=5.0)
+    assert torch.allclose(p, ref_p.data, rtol=1e-5, atol=1e-7)
+    # NaN guard: a set skip flag leaves everything untouched
+    before = p.clone()
+    K.adamw(p, g, m1, m2, 5e-5, 0.9, 0.999, 1e-8, 0.02, 4, sumsq=ss, max_norm=5.0, skip_flag=torch.ones(1, device=DEV))
+    assert torch.equal(p, before)
+
+
+def test_colsum_gather_scatter_add():
+    x = rnd(1000, 768, dtype=BF)
+    out = torch.zeros(768, device=DEV)
+    K.colsum(x, out)
+    assert rel_err(out, x.float().sum(0)) < 1e-4
+    src = rnd(12, 54, 128, dtype=BF)
+    idx = torch.tensor([3, 3, 0, 11, 7, 7, 7, 1, 2, 5, 9, 10], device=DEV, dtype=torch.int32)
+    got = K.gather_rows(src, idx, 12)
+    assert torch.equal(got, src[idx.long()])
+    dst = torch.zeros_like(src)
+    K.scatter_add_rows(dst, idx, src)
+    ref = torch.zeros(12, 54, 128, device=DEV).index_add_(0, idx.long(), src.float())
+    assert rel_err(dst, ref) < 1e-2
+    a, b = rnd(4096, dtype=BF), rnd(4096, seed=9, dtype=BF)
+    assert torch.equal(K.add_(a.clone(), b), (a.float() + b.float()).to(BF))
+
+
+# ---------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K_", [(128, 256, 64), (5184, 768, 768), (300, 768, 1000), (96, 256, 768),
+                                    (777, 2304, 768), (1000, 300, 768), (5184, 3072, 768), (2048, 768, 3072)])
+def test_gemm_kmajor(M, N, K_):
+    a, b = rnd(M, K_, dtype=BF, seed=1), rnd(N, K_, dtype=BF, seed=2, scale=0.05)
+    ldc = (N + 7) // 8 * 8
+    out = torch.zeros(M, ldc, device=DEV, dtype=BF)
+    K.gemm(a, b, M, N, K_, out=out)
+    ref = a.float() @ b.float().t()
+    assert rel_err(out[:, :N], ref) < 5e-3, rel_err(out[:, :N], ref)
+    if ldc > N:
+        assert float(out[:, N:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K_", [(256, 256, 128), (768, 3072, 5184), (300, 768, 1000), (520, 264, 777 * 8 // 8)])
+def test_gemm_mn_major(a_mn, b_mn, M, N, K_):
+    K8 = (K_ + 7) // 8 * 8
+    M8, N8 = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    A = rnd(M, K_, dtype=BF, seed=5)
+    Bm = rnd(N, K_, dtype=BF, seed=6, scale=0.05)
+    if a_mn:
+        a_store = torch.zeros(K_, M8, device=DEV, dtype=BF); a_store[:, :M] = A.t(); a = a_store[:, :M]
+    else:
+        a_store = torch.zeros(M, K8, device=DEV, dtype=BF); a_store[:, :K_] = A; a = a_store[:, :K_]
+    if b_mn:
+        b_store = torch.zeros(K_, N8, device=DEV, dtype=BF); b_store[:, :N] = Bm.t(); b = b_store[:, :N]
+    else:
+        b_store = torch.zeros(N, K8, device=DEV, dtype=BF); b_store[:, :K_] = Bm; b = b_store[:, :K_]
+    out = torch.zeros(M, N8, device=DEV, dtype=torch.float32)
+    K.gemm(a, b, M, N, K_, a_mn=a_mn, b_mn=b_mn, out=out, out_f32=True)
+    ref = A.float() @ Bm.float().t()
+    assert rel_err(out[:, :N], ref) < 2e-3, rel_err(out[:, :N], ref)
+
+
+def test_gemm_epilogues():
+    M, N, K_ = 1000, 768, 768
+    a, w = rnd(M, K_, dtype=BF, seed=1), rnd(N, K_, dtype=BF, seed=2, scale=0.05)
+    bias, res = rnd(N, seed=3), rnd(M, N, dtype=BF, seed=4)
+    ref_pre = a.float() @ w.float().t() + bias
+    # bias + residual
+    out = K.gemm(a, w, M, N, K_, bias=bias, residual=res)
+    assert rel_err(out, ref_pre + res.float()) < 5e-3
+    # bias + gelu with pre-activation store
+    pre = torch.empty(M, N, device=DEV, dtype=BF)
+    out = K.gemm(a, w, M, N, K_, bias=bias, gelu=True, pre_act_out=pre)
+    assert rel_err(pre, ref_pre) < 5e-3 and rel_err(out, F.gelu(ref_pre)) < 6e-3
+    # dgelu
+    x = rnd(M, N, dtype=BF, seed=7)
+    out = K.gemm(a, w, M, N, K_, dgelu_pre=x)
+    xf = x.float().requires_grad_(True)
+    F.gelu(xf).backward((a.float() @ w.float().t()))
+    assert rel_err(out, xf.grad) < 6e-3
+    # fp32 accumulate (wgrad into the gradient arena)
+    acc = rnd(M, N, seed=8)
+    want = acc + a.float() @ w.float().t()
+    K.gemm(a, w, M, N, K_, out=acc, out_f32=True, accumulate=True)
+    assert rel_err(acc, want) < 1e-3
+    # dropout: mask is a pure function of (seed, element) and keeps ~1-p
+    o1 = K.gemm(a, w, M, N, K_, bias=bias, dropout_p=0.1, seed=77)
+    o2 = K.gemm(a, w, M, N, K_, bias=bias, dropout_p=0.1, seed=77)
+    assert torch.equal(o1, o2)
+    kept = (o1 != 0).float().mean().item()
+    assert abs(kept - 0.9) < 0.01
+    nz = o1 != 0
+    assert rel_err(o1[nz], (ref_pre / 0.9)[nz]) < 6e-3
+
+
+# ---------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("rows,H", [(5184, 768), (333, 128), (7, 1024)])
+def test_layernorm_fwd_bwd(rows, H):
+    x = rnd(rows, H, dtype=BF, seed=1, scale=2.0)
+    g, b = 1 + 0.1 * rnd(H, seed=2), 0.1 * rnd(H, seed=3)
+    y, mean, rstd = K.layernorm_fwd(x, g, b, 1e-12)
+    xf = x.float().requires_grad_(True)
+    gf, bf = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.layer_norm(xf, (H,), gf, bf, 1e-12)
+    assert rel_err(y, ref) < 4e-3
+    dy = rnd(rows, H, dtype=BF, seed=4)
+    ref.backward(dy.float())
+    dg, db, dbias = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    dx, dxb = K.layernorm_bwd(dy, x, mean, rstd, g, dg, db, dbias=dbias)
+    assert dxb is dx
+    assert rel_err(dx, xf.grad) < 6e-3
+    assert rel_err(dg, gf.grad) < 2e-3 and rel_err(db, bf.grad) < 2e-3
+    assert rel_err(dbias, dx.float().sum(0)) < 1e-3
+
+
+def test_layernorm_dropout_consistency():
+    rows, H = 512, 768
+    x = rnd(rows, H, dtype=BF, seed=1)
+    g, b = 1 + 0.1 * rnd(H, seed=2), 0.1 * rnd(H, seed=3)
+    y0, mean, rstd = K.layernorm_fwd(x, g, b, 1e-12)
+    y1, _, _ = K.layernorm_fwd(x, g, b, 1e-12, dropout_p=0.1, seed=5)
+    keep = y1 != 0
+    assert abs(keep.float().mean().item() - 0.9) < 0.01
+    assert rel_err(y1[keep], (y0.float() / 0.9)[keep]) < 6e-3
+    # backward with the same seed masks dy identically
+    dy = rnd(rows, H, dtype=BF, seed=4)
+    dg, db = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    dx1, _ = K.layernorm_bwd(dy, x, mean, rstd, g, dg, db, out_dropout_p=0.1, out_seed=5)
+    dym = (dy.float() * keep / 0.9).to(BF)
+    dg2, db2 = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    dx2, _ = K.layernorm_bwd(dym, x, mean, rstd, g, dg2, db2)
+    assert rel_err(dx1, dx2) < 1e-2
+
+
+# ---------------------------------------------------------------- attention
+def ref_attention(q, k, v, kv_len, causal, scale):
+    # q [B,h,Tq,d] fp32 etc.
+    s = q @ k.transpose(-1, -2) * scale
+    B, h, Tq, Tk = s.shape
+    mask = torch.ones(B, 1, Tq, Tk, dtype=torch.bool, device=q.device)
+    if kv_len is not None:
+        mask = mask & (torch.arange(Tk, device=q.device)[None, None, None, :] < kv_len[:, None, None, None])
+    if causal:
+        mask = mask & (torch.arange(Tk, device=q.device)[None, None, None, :] <= torch.arange(Tq, device=q.device)[None, None, :, None])
+    s = s.masked_fill(~mask, float("-inf"))
+    return torch.softmax(s, -1) @ v
+
+
+@pytest.mark.parametrize("B,h,Tq,Tk,causal,ragged", [(4, 12, 54, 54, False, False), (3, 12, 99, 99, True, True),
+                                                     (5, 2, 54, 83, False, True), (2, 12, 83, 54, False, False),
+                                                     (2, 12, 128, 128, True, True), (3, 2, 17, 64, False, True),
+                                                     (2, 12, 54, 54, True, False)])
+def test_attention_fwd_bwd(B, h, Tq, Tk, causal, ragged):
+    H = h * 64
+    self_attn = Tq == Tk
+    if self_attn:
+        qkv = rnd(B * Tq, 3 * H, dtype=BF, seed=1)
+        q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+    else:
+        q = rnd(B * Tq, H, dtype=BF, seed=1)
+        kv = rnd(B * Tk, 2 * H, dtype=BF, seed=2)
+        k, v = kv[:, :H], kv[:, H:]
+    kv_len = None
+    if ragged:
+        kv_len = torch.randint(max(1, Tk // 4), Tk + 1, (B,), generator=torch.Generator().manual_seed(3)).to(DEV).int()
+        kv_len[0] = Tk
+    o = torch.empty(B * Tq, H, device=DEV, dtype=BF)
+    lse = torch.empty(B * h * Tq, device=DEV)
+    K.attn_fwd(q, k, v, o, lse, B, h, Tq, Tk, kv_len, causal, 0.125)
+
+    def heads(t, T):
+        return t.float().reshape(B, T, h, 64).permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+    qf, kf, vf = heads(q, Tq), heads(k, Tk), heads(v, Tk)
+    ref = ref_attention(qf, kf, vf, kv_len, causal, 0.125)
+    ref_o = ref.permute(0, 2, 1, 3).reshape(B * Tq, H)
+    assert rel_err(o, ref_o) < 8e-3, rel_err(o, ref_o)
+    do = rnd(B * Tq, H, dtype=BF, seed=4)
+    ref.backward(do.float().reshape(B, Tq, h, 64).permute(0, 2, 1, 3))
+    if self_attn:
+        dqkv = torch.zeros(B * Tq, 3 * H, device=DEV, dtype=BF)
+        dq, dk, dv = dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:]
+    else:
+        dq = torch.zeros(B * Tq, H, device=DEV, dtype=BF)
+        dkv = torch.zeros(B * Tk, 2 * H, device=DEV, dtype=BF)
+        dk, dv = dkv[:, :H], dkv[:, H:]
+    K.attn_bwd(do, q, k, v, o, lse, dq, dk, dv, B, h, Tq, Tk, kv_len, causal, 0.125)
+
+    def flat(t, T):
+        return t.permute(0, 2, 1, 3).reshape(B * T, H)
+    assert rel_err(dq, flat(qf.grad, Tq)) < 2e-2, ("dq", rel_err(dq, flat(qf.grad, Tq)))
+    assert rel_err(dk, flat(kf.grad, Tk)) < 2e-2, ("dk", rel_err(dk, flat(kf.grad, Tk)))
+    assert rel_err(dv, flat(vf.grad, Tk)) < 2e-2, ("dv", rel_err(dv, flat(vf.grad, Tk)))
+
+
+def test_attention_kv_broadcast():
+    B, h, Tq, Tk, H = 4, 12, 9, 54, 768
+    q, kv = rnd(B * Tq, H, dtype=BF, seed=1), rnd(Tk, 2 * H, dtype=BF, seed=2)
+    o = torch.empty(B * Tq, H, device=DEV, dtype=BF)
+    K.attn_fwd(q, kv[:, :H], kv[:, H:], o, None, B, h, Tq, Tk, None, False, 0.125, kv_bstride=0)
+    o2 = torch.empty_like(o)
+    kvr = kv.repeat(B, 1)
+    K.attn_fwd(q, kvr[:, :H], kvr[:, H:], o2, None, B, h, Tq, Tk, None, False, 0.125)
+    assert torch.equal(o, o2)
+
+
+# ---------------------------------------------------------------- ITC head vs the oracle restatement
+@pytest.mark.parametrize("B,Q", [(8, 96), (96, 36864), (6, 96)])
+def test_itc_matches_oracle(B, Q):
+    from oracle import spmm_ref
+    E = 256
+    z = [rnd(B, E, seed=s) for s in (1, 2, 3, 4)]
+    z[2] = z[0] + 0.05 * z[2]
+    z[3] = z[1] + 0.05 * z[3]
+    pq, tq = F.normalize(rnd(Q, E, seed=5), dim=1), F.normalize(rnd(Q, E, seed=6), dim=1)
+    temp = torch.tensor(0.07, device=DEV)
+    out = K.itc(z[0], z[1], z[2], z[3], pq, tq, temp, 0.4)
+    zp, zt = z[0].clone().requires_grad_(True), z[1].clone().requires_grad_(True)
+    tr = temp.clone().requires_grad_(True)
+    loss, s_i2t, s_t2i = spmm_ref.itc_loss(F.normalize(zp, dim=-1), F.normalize(zt, dim=-1), F.normalize(z[2], dim=-1),
+                                           F.normalize(z[3], dim=-1), pq.t().contiguous(), tq.t().contiguous(), tr, 0.4)
+    loss.backward()
+    assert abs(float(out["loss"]) - float(loss)) < 2e-5 * abs(float(loss)) + 1e-5
+    assert rel_err(out["dz_prop"], zp.grad) < 1e-4 and rel_err(out["dz_text"], zt.grad) < 1e-4
+    assert abs(float(out["dtemp"]) - float(tr.grad)) < 1e-3 * abs(float(tr.grad)) + 1e-5
+    assert torch.allclose(out["sim_i2t"], s_i2t[:, :B].detach(), atol=1e-4)
+    assert torch.allclose(out["sim_t2i"], s_t2i[:, :B].detach(), atol=1e-4)
+    assert torch.allclose(out["feat_prop_m"], F.normalize(z[2], dim=-1), atol=1e-6)
+    assert float(out["nan_flag"]) == 0.0
+
+
+def test_sampler_matches_cpu_replica_and_enqueue():
+    from oracle import sampler_ref
+    B = 96
+    s1, s2 = rnd(B, B, seed=1, scale=3.0), rnd(B, B, seed=2, scale=3.0)
+    for step in (0, 1, 12345678901):
+        t2i, i2t = K.sample_negatives(s1, s2, 0xDEADBEEFCAFE, step)
+        rt2i, ri2t = sampler_ref.sample_negatives(s1.cpu().numpy(), s2.cpu().numpy(), 0xDEADBEEFCAFE, step)
+        assert t2i.tolist() == rt2i and i2t.tolist() == ri2t
+        assert all(t2i[b] != b and i2t[b] != b for b in range(B))
+    Q, E = 960, 256
+    pq, tq = rnd(Q, E, seed=3), rnd(Q, E, seed=4)
+    pf, tf = rnd(192, E, seed=5), rnd(192, E, seed=6)
+    ptr = torch.tensor([768], device=DEV)
+    ref_p = pq.clone(); ref_p[768:960] = pf
+    K.enqueue(pq, tq, pf, tf, ptr)
+    assert torch.equal(pq, ref_p) and int(ptr) == 0
+    K.enqueue(pq, tq, pf, tf, ptr, skip_flag=torch.ones(1, device=DEV))
+    assert int(ptr) == 0
+    K.enqueue(pq, tq, tf, pf, ptr)
+    assert torch.equal(pq[:192], tf) and torch.equal(tq[:192], pf) and int(ptr) == 192
+
+
+# ---------------------------------------------------------------- losses
+def test_lm_loss():
+    B, L, V, ld = 8, 40, 300, 320
+    logits = torch.zeros(B * L, ld, device=DEV, dtype=BF); logits[:, :V] = rnd(B * L, V, dtype=BF, seed=1, scale=2.0)
+    teacher = torch.zeros(B * L, ld, device=DEV, dtype=BF); teacher[:, :V] = rnd(B * L, V, dtype=BF, seed=2, scale=2.0)
+    ids = torch.randint(4, V, (B, L), generator=torch.Generator().manual_seed(3))
+    ids[:, 0] = 2
+    ids[2, 20:] = 0; ids[5, 33:] = 0
+    ids = ids.to(DEV)
+    loss, dlog = K.lm_loss(logits, teacher, ids, V, 0.4)
+    lf = logits[:, :V].float().reshape(B, L, V).requires_grad_(True)
+    tf = teacher[:, :V].float().reshape(B, L, V)
+    lab = ids[:, 1:]
+    ce = F.cross_entropy(lf[:, :-1].permute(0, 2, 1), lab)
+    ds = -torch.sum(F.log_softmax(lf[:, :-1], -1) * F.softmax(tf[:, :-1], -1), -1)
+    ref = 0.6 * ce + 0.4 * ds[lab != 0].mean()
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-4 * abs(float(ref))
+    assert rel_err(dlog[:, :V].reshape(B, L, V), lf.grad) < 8e-3
+    assert float(dlog[:, V:].abs().max()) == 0.0
+
+
+def test_itm_and_mpm_losses():
+    B, H = 8, 768
+    x = rnd(3 * B, 2 * H, dtype=BF, seed=1)
+    w, b = rnd(2, 2 * H, seed=2, scale=0.05), rnd(2, seed=3, scale=0.1)
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    loss, dx = K.itm_loss(x, w, b, B, dw, db)
+    xf, wf, bf = x.float().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    labels = torch.cat([torch.ones(B), torch.zeros(2 * B)]).long().to(DEV)
+    ref = F.cross_entropy(F.linear(xf, wf, bf), labels)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5
+    assert rel_err(dx, xf.grad) < 6e-3 and rel_err(dw, wf.grad) < 1e-4 and rel_err(db, bf.grad) < 1e-4
+
+    n_prop = 53
+    t = rnd(B * (n_prop + 1), H, dtype=BF, seed=4)
+    w2, b2 = rnd(1, H, seed=5, scale=0.05), rnd(1, seed=6)
+    pv = rnd(B, n_prop, seed=7)
+    mpm = (rnd(B, n_prop, seed=8) > 0).float()
+    dw2, db2 = torch.zeros_like(w2), torch.zeros_like(b2)
+    loss, dt = K.mpm_loss(t, w2, b2, pv, mpm, dw2, db2)
+    tf, wf, bf = t.float().requires_grad_(True), w2.clone().requires_grad_(True), b2.clone().requires_grad_(True)
+    pred = F.linear(tf.reshape(B, n_prop + 1, H)[:, :-1], wf, bf).squeeze(-1)
+    keep = (1 - mpm).bool()
+    ref = 5 * F.mse_loss(pred[keep], pv[keep])
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-4 * abs(float(ref))
+    assert rel_err(dt, tf.grad) < 6e-3 and rel_err(dw2, wf.grad) < 1e-4 and rel_err(db2, bf.grad) < 1e-4
+
+
+# ---------------------------------------------------------------- embeddings
+def test_embedding_kernels():
+    B, T, H, V = 6, 40, 768, 300
+    ids = torch.randint(0, V, (B, T), generator=torch.Generator().manual_seed(1)).to(DEV)
+    word, pos, typ = rnd(V, H, seed=2, scale=0.02), rnd(512, H, seed=3, scale=0.02), rnd(2, H, seed=4, scale=0.02)
+    x = K.embed_text_fwd(ids, word, pos, typ[0], H)
+    ref = word[ids] + typ[0] + pos[:T]
+    assert rel_err(x.reshape(B, T, H), ref) < 4e-3
+    dx = rnd(B * T, H, dtype=BF, seed=5)
+    dword, dpos, dtyp = torch.zeros_like(word), torch.zeros_like(pos), torch.zeros(H, device=DEV)
+    K.embed_text_bwd(dx, ids, dword, dpos, dtyp, 0)
+    d = dx.float().reshape(B, T, H)
+    ref_w = torch.zeros_like(word).index_put_((ids.reshape(-1),), d.reshape(-1, H), accumulate=True)
+    ref_w[0] = 0
+    assert rel_err(dword, ref_w) < 1e-5 and rel_err(dpos[:T], d.sum(0)) < 1e-5 and rel_err(dtyp, d.sum((0, 1))) < 1e-5
+    # PV tokeniser
+    n_prop = 53
+    pv, mpm = rnd(B, n_prop, seed=6), (rnd(B, n_prop, seed=7) > 0).float()
+    w, b, cls, mtok = rnd(H, seed=8), rnd(H, seed=9), rnd(H, seed=10), rnd(H, seed=11)
+    props = K.pv_tokens_fwd(pv, mpm, w, b, cls, mtok)
+    wf, bf, cf, mf = [t.clone().requires_grad_(True) for t in (w, b, cls, mtok)]
+    feat = pv[:, :, None] * wf + bf
+    refp = torch.cat([cf.expand(B, 1, H), feat * (1 - mpm[:, :, None]) + mf * mpm[:, :, None]], 1)
+    assert rel_err(props, refp) < 4e-3
+    dp = rnd(B, n_prop + 1, H, dtype=BF, seed=12)
+    refp.backward(dp.float())
+    dw, db_, dc, dm = [torch.zeros(H, device=DEV) for _ in range(4)]
+    K.pv_tokens_bwd(dp, pv, mpm, dw, db_, dc, dm)
+    for got, want in ((dw, wf.grad), (db_, bf.grad), (dc, cf.grad), (dm, mf.grad)):
+        assert rel_err(got, want) < 1e-5
+    xin = K.embed_inputs_fwd(props, pos, typ[0])
+    assert rel_err(xin.reshape(B, n_prop + 1, H), props.float() + typ[0] + pos[:n_prop + 1]) < 4e-3
+    dpos2, dtyp2 = torch.zeros_like(pos), torch.zeros(H, device=DEV)
+    K.embed_inputs_bwd(dp.reshape(-1, H), n_prop + 1, dpos2, dtyp2)
+    assert rel_err(dpos2[:n_prop + 1], dp.float().sum(0)) < 1e-5 and rel_err(dtyp2, dp.float().sum((0, 1))) < 1e-5
