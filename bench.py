@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""SPMM pre-training step benchmark (BASELINE.json metric: pretrain molecules/sec on 1/2/4/8 B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--seq-len L] [--ragged]
+
+One "step" = the body of the reference's training_step (SPMM_models.py:348-362): zero_grad -> SPMM.forward (EMA,
+all encoder passes, 4 loss heads, enqueue) -> backward -> gradient all-reduce -> clip_grad_norm_(5.) -> AdamW, on
+the reference's config_bert*.json shapes with B=96 molecules per GPU, queue 36864, train mode (dropout on), bf16
+tensor-core GEMMs with fp32 master weights, synthetic BPE-300 ids + N(0,1) property vectors, name-seeded weights.
+N>1 is launched by torchrun (one rank per GPU, NCCL); weak scaling (per-GPU batch fixed).
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` feeds pinned HOST
+batches through the public API each step and reads the losses back.  `roofline` is for the dominant kernel (the
+tcgen05 GEMM, tensor-bound) measured with CUDA events around every launch of one extra instrumented step;
+`cpu_baseline` is the oracle port of the reference path timed on the host cores on a bounded sample.
+`--impl reference` times that CPU path alone (the reference's own algorithm; /root/reference is not on the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+CFG = os.path.join(REPO, "spmm_b200", "configs")
+H, I, E, P_TOK, V = 768, 3072, 256, 54, 300
+
+
+def flops_per_molecule(l, B, Q):
+    """SURVEY.md section 8d (validated against torch FlopCounter on the reference to 5 digits)."""
+    S = lambda T, K: T * (24 * H * H + 4 * K * H)
+    X = lambda Tq, Tk: 4 * H * H * (Tq + Tk) + 4 * Tq * Tk * H
+    F_ = lambda Tq, Tk: S(Tq, Tq) + X(Tq, Tk)
+    P = P_TOK
+    head = 2 * l * (2 * H * H + 2 * H * V) + P * (2 * H * H + 2 * H) + 4 * 2 * H * E + 3 * 2 * (2 * H) * 2 + 8 * 2 * E * (B + Q)
+    fwd_all = 6 * (3 * S(P, P) + 4 * S(l, l) + 4 * F_(P, l) + 5 * F_(l, P)) + head
+    fwd_grad = 6 * (2 * S(P, P) + 2 * S(l, l) + 4 * F_(P, l) + 4 * F_(l, P)) + head / 2
+    return fwd_all + 2 * fwd_grad
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_reference_steps(steps, warmup, batch, seq_len, ragged, queue=36864):
+    """Times the reference algorithm (oracle/spmm_ref.py, pinned to the unmodified reference by tests/test_oracle.py)
+    on the host cores: fp32, train-step body = forward + backward + clip + AdamW.  Returns (molecules/s, ms/step, cores)."""
+    import torch
+    from oracle import spmm_ref
+    from spmm_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ct = json.load(open(os.path.join(CFG, "config_bert.json")))
+    cp = json.load(open(os.path.join(CFG, "config_bert_property.json")))
+    keys = torch.load(os.path.join(REPO, "tests", "golden", "full_b8.pt"), weights_only=False)["state_dict_keys"]
+    keys = [(k, (s if not k.endswith("queue") else (s[0], queue)), d) for k, s, d in keys]
+    P = synth.state_from_keys(keys)
+    frozen = ("property_encoder_m.", "text_encoder_m.", "property_proj_m.", "text_proj_m.")
+    leaves, seen = [], set()
+    for k, v in P.items():
+        if v.is_floating_point() and not k.startswith(frozen) and not k.endswith("queue") and id(v) not in seen:
+            seen.add(id(v))
+            v.requires_grad_(True)
+            leaves.append(v)
+    opt = torch.optim.AdamW(leaves, lr=5e-5, weight_decay=0.02)
+    pv, ids, mask, _ = synth.synthetic_batch(batch, seed=1234, fixed_len=None if ragged else seq_len)
+    times, ptr = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        mpm = torch.bernoulli(torch.full_like(pv, 0.5))
+        losses, aux = spmm_ref.forward(P, ct, cp, pv, ids, mask, 0.4, mpm, queue_ptr=ptr,
+                                       sampler=lambda wt, wi: ([int(torch.multinomial(w, 1)) for w in wt],
+                                                               [int(torch.multinomial(w, 1)) for w in wi]))
+        ptr = aux["queue_ptr"]
+        sum(losses).backward()
+        torch.nn.utils.clip_grad_norm_(leaves, 5.0)
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * statistics.median(times)
+    return batch / (ms / 1e3), ms, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = 8
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    val, ms, cores = cpu_reference_steps(steps, warmup, B, args.seq_len, args.ragged)
+    line = {"impl": "reference", "metric": "pretrain molecules/sec", "value": val, "unit": "molecules/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, B, 1),
+            "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": cores, "kind": "port",
+                             "sample": "%d timed step(s) of batch %d (full queue 36864, fp32, fwd+bwd+clip+AdamW) on the host cores" % (steps, B)},
+            "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, B, world):
+    return {"workload": "SPMM pretrain step, reference config_bert*.json shapes (12L text/fusion + 6L PV encoder, H768), "
+                        "batch %d molecules/GPU, %s, 53-dim PV, momentum queue 36864x256, alpha 0.4, train mode (dropout 0.1)"
+                        % (B, "ragged SMILES lengths U{12..99}" if args.ragged else "SMILES length %d" % args.seq_len),
+            "global_batch": B * world, "seq_len": None if args.ragged else args.seq_len, "parallelism": "dp%d" % world,
+            "l2": "working set per step (0.58 GB bf16 weights + 2.9 GB fp32 arenas + activations) >> 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from spmm_b200 import _lib, kernels, ops, synth, trainer
+    from spmm_b200.SPMM_models import SPMM
+    from spmm_b200.optim import FusedClipAdamW
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    cfg = synth.pretrain_config(os.path.join(CFG, "config_bert.json"), os.path.join(CFG, "config_bert_property.json"),
+                                queue_size=36864, batch_size=B)
+    torch.manual_seed(0)
+    model = SPMM(config=cfg)
+    synth.fill_by_name(model)
+    model.to(dev)
+    model.build_arenas(dev)
+    model.train()
+    opt = FusedClipAdamW(model, lr=5e-5, weight_decay=0.02)
+    ops.manual_seed(999 + rank)
+    torch.manual_seed(999 + rank)
+    pv_h, ids_h, mask_h, lens = synth.synthetic_batch(B, seed=1234 + rank, fixed_len=None if args.ragged else args.seq_len)
+    pv_h, ids_h, mask_h = pv_h.pin_memory(), ids_h.pin_memory(), mask_h.pin_memory()
+    pv, ids, mask = pv_h.to(dev), ids_h.to(dev), mask_h.to(dev)
+    alpha = 0.4
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return trainer.train_step(model, opt, pv, ids, mask, alpha)
+
+    def step_e2e():
+        a, b, c = pv_h.to(dev, non_blocking=True), ids_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True)
+        losses = trainer.train_step(model, opt, a, b, c, alpha)
+        return torch.stack(losses).cpu()
+
+    for _ in range(args.warmup):
+        last = step_resident()
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        last = step_resident()
+    e1.record()
+    sync()
+    launches = _lib.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    losses = [float(x) for x in last]
+
+    # end-to-end through the public API with host batches
+    step_e2e()
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        host_losses = step_e2e()
+    e1.record()
+    sync()
+    ms_e2e = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+
+    roof, extra = None, None
+    if rank == 0:
+        roof, extra = kernel_rooflines(torch, kernels, model, step_resident, B, world)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step / 1e3)
+    l_eff = statistics.mean(lens)
+    fl = sum(flops_per_molecule(l, B, 36864) for l in lens) * world
+    line = {"metric": "pretrain molecules/sec", "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B, world),
+            "e2e": {"value": B * world / (ms_e2e / args.steps / 1e3), "unit": "molecules/s",
+                    "h2d_bytes_per_step": (pv_h.numel() * 4 + ids_h.numel() * 8 + mask_h.numel() * 8),
+                    "d2h_bytes_per_step": 16},
+            "gpu_launches": launches, "clocks": clocks, "losses_last_step": losses,
+            "step_tflops": fl / (ms_step / 1e3) / 1e12,
+            "step_frac_of_bf16_sustained": fl / (ms_step / 1e3) / 1e12 / (pk["bf16_tflops_sustained"] * world),
+            "roofline": roof, "roofline_extra": extra, "peaks": pk}
+    if world == 1 and not args.no_cpu_baseline:
+        v, ms_cpu, cores = cpu_reference_steps(1, 1, 8, args.seq_len, args.ragged)
+        line["cpu_baseline"] = {"value": v, "unit": "molecules/s", "cores": cores, "kind": "port",
+                                "sample": "1 timed step (after 1 warm-up) of batch 8, full queue 36864, fp32 fwd+bwd+clip+AdamW, "
+                                          "oracle/spmm_ref.py on the host cores (%.1f s/step)" % (ms_cpu / 1e3)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_rooflines(torch, kernels, model, step_fn, B, world):
+    """One extra instrumented step: CUDA events (current stream) around every GEMM / EMA / ITC launch."""
+    pk = peaks()
+    rec = {"gemm": [], "ema": [], "itc": []}
+    orig = {"gemm": kernels.gemm, "ema": kernels.ema, "itc": kernels.itc}
+
+    def wrap(name, work):
+        fn = orig[name]
+
+        def inner(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a, **k)
+            e.record()
+            rec[name].append((s, e, work(*a, **k)))
+            return r
+        return inner
+    kernels.gemm = wrap("gemm", lambda a, b, M, N, K_, **k: 2.0 * M * N * K_)
+    kernels.ema = wrap("ema", lambda p, pm, pb, pmb, mom: 16.0 * p.numel())             # 8 B read + 4 B + 2x2 B written
+    kernels.itc = wrap("itc", lambda zp, zt, zpm, ztm, pq, tq, temp, alpha: 2.0 * 2 * pq.numel() * 4)  # fwd + bwd scan of both queues
+    try:
+        step_fn()
+        torch.cuda.synchronize()
+    finally:
+        kernels.gemm, kernels.ema, kernels.itc = orig["gemm"], orig["ema"], orig["itc"]
+    tot = {k: (sum(s.elapsed_time(e) for s, e, _ in v), sum(w for _, _, w in v), len(v)) for k, v in rec.items()}
+    g_ms, g_fl, g_n = tot["gemm"]
+    ach = g_fl / (g_ms / 1e3) / 1e12
+    roof = {"kernel": "gemm_bf16_kernel (tcgen05.mma + TMA, all fwd/dgrad/wgrad GEMMs of one step)", "bound": "tensor",
+            "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+            "traffic": None, "launches": g_n, "ms_per_step_in_kernel": g_ms, "flops_per_step": g_fl,
+            "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)"}
+    extra = {}
+    for name, label, unit_bytes in (("ema", "ema_kernel (EMA + bf16 shadows, 16 B/param)", True),
+                                    ("itc", "itc_pass_kernel x2 (+normalize/combine/finish): queue streamed twice", True)):
+        ms, by, n = tot[name]
+        if n:
+            gbs = by / (ms / 1e3) / 1e9
+            extra[name] = {"kernel": label, "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                           "frac": gbs / pk["hbm_gbs"], "traffic": None, "ms": ms, "algorithmic_bytes": by}
+    return roof, extra
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=96)
+    ap.add_argument("--seq-len", type=int, default=64)
+    ap.add_argument("--ragged", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

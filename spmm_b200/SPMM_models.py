@@ -1,0 +1,294 @@
+"""Drop-in `SPMM` for the reference's SPMM_models.py (jinhojsk515/spmm), B200-native underneath.
+
+Same constructor, `forward(property_original, text_input_ids, text_attention_mask, alpha)` signature, sub-module
+attribute tree and state-dict keys as the reference class (SPMM_models.py:16-399), so SPMM_pretrain.py and the
+d_*.py scripts can import this module instead.  What differs is everything below the Python surface:
+
+  * parameters live in flat HBM arenas (spmm_b200/arena.py); the momentum EMA is one kernel,
+  * every encoder block / loss head is a short sequence of hand-written sm_100a kernels (spmm_b200/ops.py),
+  * the 2B+8 host syncs of the reference forward are gone: hard negatives are drawn on the device by a
+    counter-based sampler, `queue_ptr` advances on the device, the NaN guard is a device flag consumed by the
+    enqueue and optimiser kernels,
+  * the momentum queues are stored key-major [Q, E]; `state_dict()` still exposes `prop_queue` / `text_queue` as
+    [E, Q] like the reference (SPMM_models.py:72-73).
+
+There is no CPU or PyTorch-eager fallback: without the CUDA library the forward raises.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+from . import arena as arena_mod
+from . import kernels as K
+from . import ops
+from .xbert import BertConfig, BertForMaskedLM, MaskInfo
+
+try:                                       # pytorch_lightning is optional (absent in this image)
+    import pytorch_lightning as pl
+    _Base = pl.LightningModule
+except Exception:                          # noqa: BLE001
+    _Base = nn.Module
+
+
+def gather_world_feats(feats):
+    """concat_all_gather (reference SPMM_models.py:389-399) for a stacked [2, B, E] feature tensor: ONE collective for
+    both modalities; result [2, W*B, E] with rank r's rows at [r*B, (r+1)*B) exactly like torch.cat(tensors_gather)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return feats
+    W_ = dist.get_world_size()
+    feats = feats.contiguous()
+    if dist.get_backend() == "nccl":
+        gathered = torch.empty((W_,) + tuple(feats.shape), device=feats.device, dtype=feats.dtype)
+        dist.all_gather_into_tensor(gathered, feats)
+    else:
+        parts = [torch.empty_like(feats) for _ in range(W_)]
+        dist.all_gather(parts, feats)
+        gathered = torch.stack(parts)
+    return gathered.permute(1, 0, 2, 3).reshape(2, -1, feats.shape[-1]).contiguous()
+
+
+class AttrDict(dict):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.__dict__ = self
+
+
+class SPMM(_Base):
+    def __init__(self, tokenizer=None, config=None, loader_len=0, no_train=False):
+        super().__init__()
+        self.automatic_optimization = False
+        self.config = config
+        self.tokenizer = tokenizer
+        self.training_step_outputs = []
+        embed_dim = config['embed_dim']
+
+        bert_config = BertConfig.from_json_file(config['bert_config_text'])
+        self.text_encoder = BertForMaskedLM(config=bert_config)
+        text_width = self.text_encoder.config.hidden_size
+        property_width = text_width
+        self.property_proj = nn.Linear(property_width, embed_dim)
+        self.text_proj = nn.Linear(text_width, embed_dim)
+        self.itm_head = nn.Linear(text_width * 2, 2)
+        self.property_embed = nn.Linear(1, property_width)
+        bert_config2 = BertConfig.from_json_file(config['bert_config_property'])
+        self.property_encoder = BertForMaskedLM(config=bert_config2).bert
+        self.property_mtr_head = nn.Sequential(nn.Linear(property_width, property_width), nn.GELU(),
+                                               nn.LayerNorm(property_width, bert_config.layer_norm_eps),
+                                               nn.Linear(property_width, 1))
+        self.property_cls = nn.Parameter(torch.zeros(1, 1, property_width))
+        self.property_mask = nn.Parameter(torch.zeros(1, 1, property_width))
+
+        self.property_encoder_m = BertForMaskedLM(config=bert_config2).bert
+        self.property_proj_m = nn.Linear(property_width, embed_dim)
+        self.text_encoder_m = BertForMaskedLM(config=bert_config)
+        self.text_proj_m = nn.Linear(text_width, embed_dim)
+        self.model_pairs = [[self.property_encoder, self.property_encoder_m], [self.property_proj, self.property_proj_m],
+                            [self.text_encoder, self.text_encoder_m], [self.text_proj, self.text_proj_m]]
+        self.copy_params()
+
+        self.no_train = no_train
+        self.embed_dim = embed_dim
+        self.momentum = 0.995
+        self.queue_size = 0
+        if not no_train:
+            self.temp = nn.Parameter(torch.ones([]) * config['temp'])
+            self.mlm_probability = config['mlm_probability']
+            self.warmup_steps = config['schedular']['warmup_epochs']
+            self.loader_len = loader_len
+            self.momentum = config['momentum']
+            self.queue_size = config['queue_size']
+            # key-major storage [Q, E]; the reference's [E, Q] view is `self.prop_queue` / state_dict()
+            self.register_buffer("prop_queue_km", F.normalize(torch.randn(self.queue_size, embed_dim), dim=1), persistent=False)
+            self.register_buffer("text_queue_km", F.normalize(torch.randn(self.queue_size, embed_dim), dim=1), persistent=False)
+            self.register_buffer("queue_ptr", torch.zeros(1, dtype=torch.long))
+        else:
+            self.temp = None
+        self._register_state_dict_hook(SPMM._queues_to_state_dict)
+        self._register_load_state_dict_pre_hook(self._queues_from_state_dict)
+        self.register_load_state_dict_post_hook(SPMM._after_load)
+        self._arena = None
+        self._step = 0
+        self.sampler_seed = 0x5EED
+        self.last_aux = {}
+
+    # ------------------------------------------------------------------ reference-compatible queue surface
+    @property
+    def prop_queue(self):
+        return self.prop_queue_km.t()
+
+    @property
+    def text_queue(self):
+        return self.text_queue_km.t()
+
+    @staticmethod
+    def _queues_to_state_dict(module, state_dict, prefix, local_metadata):
+        if not module.no_train:
+            state_dict[prefix + "prop_queue"] = module.prop_queue_km.t().contiguous()
+            state_dict[prefix + "text_queue"] = module.text_queue_km.t().contiguous()
+        return state_dict
+
+    def _queues_from_state_dict(self, state_dict, prefix, *args):
+        for k in ("prop_queue", "text_queue"):
+            v = state_dict.pop(prefix + k, None)
+            if v is not None and not self.no_train:
+                with torch.no_grad():
+                    getattr(self, k + "_km").copy_(v.t())
+
+    @staticmethod
+    def _after_load(module, incompatible):
+        for k in ("prop_queue", "text_queue"):
+            if k in incompatible.unexpected_keys:
+                incompatible.unexpected_keys.remove(k)
+        if module._arena is not None and module._arena.valid_for(module):
+            module._arena.refresh_shadows(ema=False)
+
+    # ------------------------------------------------------------------ arenas
+    def build_arenas(self, device=None):
+        """Moves every parameter into the flat arenas on `device` and builds the kernel-facing views."""
+        device = torch.device(device) if device is not None else next(self.parameters()).device
+        if device.type != "cuda":
+            raise K._lib.SpmmKernelError("spmm_b200 runs on CUDA (sm_100a) only: there is no CPU fallback")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        super().to(device)
+        A = arena_mod.ParamArena(self, device)
+        anchor = torch.zeros(1, device=device, requires_grad=True)
+        arena_mod.bert_bundles(A, "text_encoder.bert", self.text_encoder.bert, False, anchor, "text_encoder.cls.predictions")
+        arena_mod.bert_bundles(A, "text_encoder_m.bert", self.text_encoder_m.bert, True, anchor, "text_encoder.cls.predictions")
+        arena_mod.bert_bundles(A, "property_encoder", self.property_encoder, False, anchor, is_property=True)
+        arena_mod.bert_bundles(A, "property_encoder_m", self.property_encoder_m, True, anchor, is_property=True)
+        W = {}
+        for n in ("property_proj", "text_proj"):
+            W[n] = arena_mod.linear_bundle(A, n)
+            W[n + "_m"] = arena_mod.linear_bundle(A, n + "_m", momentum=True)
+        ns = arena_mod.SimpleNamespace
+        W["pv"] = ns(w=A.f32("property_embed.weight").view(-1), b=A.f32("property_embed.bias"),
+                     cls=A.f32("property_cls").view(-1), mask=A.f32("property_mask").view(-1),
+                     g_w=A.grad("property_embed.weight").view(-1), g_b=A.grad("property_embed.bias"),
+                     g_cls=A.grad("property_cls").view(-1), g_mask=A.grad("property_mask").view(-1))
+        W["itm"] = ns(w=A.f32("itm_head.weight"), b=A.f32("itm_head.bias"), g_w=A.grad("itm_head.weight"),
+                      g_b=A.grad("itm_head.bias"))
+        eps = self.property_mtr_head[2].eps
+        W["mtr"] = ns(eps=eps, w0=A.w16("property_mtr_head.0.weight"), b0=A.f32("property_mtr_head.0.bias"),
+                      ln_g=A.f32("property_mtr_head.2.weight"), ln_b=A.f32("property_mtr_head.2.bias"),
+                      w3=A.f32("property_mtr_head.3.weight"), b3=A.f32("property_mtr_head.3.bias"),
+                      g_w0=A.grad("property_mtr_head.0.weight"), g_b0=A.grad("property_mtr_head.0.bias"),
+                      g_ln_g=A.grad("property_mtr_head.2.weight"), g_ln_b=A.grad("property_mtr_head.2.bias"),
+                      g_w3=A.grad("property_mtr_head.3.weight"), g_b3=A.grad("property_mtr_head.3.bias"))
+        self._arena, self._W, self._anchor = A, W, anchor
+        return A
+
+    def arena(self):
+        if self._arena is None or not self._arena.valid_for(self):
+            self.build_arenas(next(self.parameters()).device)
+        return self._arena
+
+    # ------------------------------------------------------------------ the hot path
+    def forward(self, property_original, text_input_ids, text_attention_mask, alpha=0, mpm_mask=None, neg_idx=None):
+        """Reference SPMM_models.py:79-256.  `mpm_mask` / `neg_idx=(neg_t2i, neg_i2t)` inject the random draws
+        (parity tests); otherwise torch.bernoulli on the device and the counter-based sampler are used."""
+        A = self.arena()
+        A.ensure_grads()
+        W = self._W
+        with torch.no_grad():
+            self.temp.clamp_(0.01, 0.5)
+            # _momentum_update (:99,265-269) hoisted to the top: identical result (momentum weights are not read
+            # before this point, online weights do not change inside forward) and it refreshes the bf16 shadows
+            A.refresh_shadows(ema=True, momentum=self.momentum)
+        pv = property_original.float().contiguous()
+        B = pv.shape[0]
+        H = self.text_encoder.config.hidden_size
+        if mpm_mask is None:
+            mpm_mask = torch.bernoulli(torch.ones_like(pv) * 0.5)          # :85, same torch generator call
+        mpm_mask = mpm_mask.float().contiguous()
+        tmask = MaskInfo(text_attention_mask)
+        ids = text_input_ids.contiguous()
+        te, te_m = self.text_encoder, self.text_encoder_m
+
+        properties = ops.pv_tokens(pv, mpm_mask, W["pv"], self._anchor)                                # :82-88
+        prop_embeds = self.property_encoder(inputs_embeds=properties).last_hidden_state                 # :90
+        z_prop = ops.proj_f32(prop_embeds[:, 0, :], W["property_proj"])                                 # :92
+        text_embeds = te.bert(ids, attention_mask=tmask, mode='text').last_hidden_state                 # :94
+        z_text = ops.proj_f32(text_embeds[:, 0, :], W["text_proj"])                                     # :95
+        with torch.no_grad():                                                                           # :98-106
+            prop_embeds_m = self.property_encoder_m(inputs_embeds=properties).last_hidden_state
+            z_prop_m = ops.proj_f32(prop_embeds_m[:, 0, :], W["property_proj_m"])
+            text_embeds_m = te_m.bert(ids, attention_mask=tmask, mode='text').last_hidden_state
+            z_text_m = ops.proj_f32(text_embeds_m[:, 0, :], W["text_proj_m"])
+        side = {}
+        loss_ita = ops.itc(z_prop, z_text, self.temp, z_prop_m, z_text_m, self.prop_queue_km, self.text_queue_km,
+                           float(alpha), side)                                                          # :102-131
+        nan_flag = side["nan_flag"]
+
+        # ================ ITM (:135-206) ================ #
+        def fusion(q, q_mask, kv, kv_mask, dec=False):
+            return te.bert(encoder_embeds=q, attention_mask=q_mask, encoder_hidden_states=kv,
+                           encoder_attention_mask=kv_mask, is_decoder=dec, mode='fusion').last_hidden_state
+        pos_prop = fusion(prop_embeds, None, text_embeds, tmask)[:, 0, :]
+        pos_text = fusion(text_embeds, tmask, prop_embeds, None)[:, 0, :]
+        if neg_idx is None:
+            self._step += 1
+            neg_t2i, neg_i2t = ops.sample_negatives(side, self.sampler_seed, self._step)                # :154-178
+        else:
+            neg_t2i = torch.as_tensor(neg_idx[0], device=pv.device, dtype=torch.int32)
+            neg_i2t = torch.as_tensor(neg_idx[1], device=pv.device, dtype=torch.int32)
+        prop_neg = ops.gather_rows(prop_embeds, neg_t2i)
+        text_neg = ops.gather_rows(text_embeds, neg_i2t)
+        tmask_all = MaskInfo(kv_len=torch.cat([tmask.kv_len, tmask.kv_len[neg_i2t.long()]]))
+        text_all = torch.cat([text_embeds, text_neg], dim=0)
+        prop_all = torch.cat([prop_neg, prop_embeds], dim=0)
+        neg_prop = fusion(prop_all, None, text_all, tmask_all)[:, 0, :]
+        neg_text = fusion(text_all, tmask_all, prop_all, None)[:, 0, :]
+        vl = torch.cat([torch.cat([pos_prop, pos_text], dim=-1), torch.cat([neg_prop, neg_text], dim=-1)], dim=0)
+        loss_itm = ops.itm_loss(vl, W["itm"], B)
+
+        self._dequeue_and_enqueue(side["feat_prop_m"], side["feat_text_m"], nan_flag)                   # :208
+
+        # ================ MLM (:210-238) ================ #
+        V = te.config.vocab_size
+        with torch.no_grad():
+            h_m = te_m.bert(ids, attention_mask=tmask, encoder_hidden_states=prop_embeds_m, is_decoder=True).last_hidden_state
+            logits_m = ops.lm_logits(h_m.view(-1, H), te_m.bert._bundles().head, V, te.logit_ld())
+        h = te.bert(ids, attention_mask=tmask, encoder_hidden_states=prop_embeds, is_decoder=True).last_hidden_state
+        loss_mlm = ops.lm_head_loss(h.view(-1, H), logits_m, ids, te.bert._bundles().head, float(alpha), V)
+
+        # ================ MPM (:240-254) ================ #
+        pc = self.property_encoder(inputs_embeds=properties, is_decoder=True).last_hidden_state
+        po = fusion(pc, None, text_embeds, tmask, dec=True)
+        loss_mpm = ops.mtr_head_loss(po.view(-1, H), pv, mpm_mask, W["mtr"])      # already x5 (:256)
+
+        self.last_aux = {"neg_t2i": neg_t2i, "neg_i2t": neg_i2t, "nan_flag": nan_flag, "mpm_mask": mpm_mask}
+        # NaN guard (:132-133) without a host sync: zero losses, and the flag disables enqueue + optimiser step
+        bad = nan_flag > 0
+        zero = torch.zeros((), device=pv.device)
+        return tuple(torch.where(bad, zero, l) for l in (loss_mlm, loss_mpm, loss_ita, loss_itm))
+
+    @torch.no_grad()
+    def copy_params(self):
+        for model_pair in self.model_pairs:
+            for param, param_m in zip(model_pair[0].parameters(), model_pair[1].parameters()):
+                param_m.data.copy_(param.data)
+                param_m.requires_grad = False
+
+    @torch.no_grad()
+    def _momentum_update(self):
+        """SPMM_models.py:265-269 as one arena kernel (bit-exact fp32)."""
+        self.arena().refresh_shadows(ema=True, momentum=self.momentum)
+
+    @torch.no_grad()
+    def _dequeue_and_enqueue(self, prop_feat, text_feat, skip_flag=None):
+        """SPMM_models.py:271-286.  Rank-local feats are all-gathered (one NCCL call for both modalities)."""
+        feats = gather_world_feats(torch.stack([prop_feat, text_feat]))     # [2, W*B, E] fp32, rank-major like torch.cat
+        n = feats.shape[1]
+        assert self.queue_size % n == 0                                      # :279
+        K.enqueue(self.prop_queue_km, self.text_queue_km, feats[0], feats[1], self.queue_ptr, skip_flag)
+
+    # ------------------------------------------------------------------ optimiser / Lightning-style hooks
+    def configure_optimizers(self):
+        from .optim import FusedClipAdamW
+        from .scheduler import create_scheduler
+        arg_opt = self.config['optimizer']
+        optimizer = FusedClipAdamW(self, lr=arg_opt['lr'], weight_decay=arg_opt['weight_decay'], max_norm=5.0)
+        scheduler, _ = create_scheduler(AttrDict(self.config['schedular']), optimizer)
+        return [optimizer], [scheduler]

@@ -75,7 +75,23 @@ def lib():
     return _lib
 
 
+# kernels launched per C call (for bench.py's `gpu_launches` claim)
+KERNELS_PER_CALL = {"spmm_itc_fwd_bwd": 5, "spmm_lm_loss_fwd_bwd": 3, "spmm_mpm_loss_fwd_bwd": 3, "spmm_enqueue": 2}
+_launches = 0
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def launch_count():
+    return _launches
+
+
 def call(name, *args):
+    global _launches
+    _launches += KERNELS_PER_CALL.get(name, 1)
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise SpmmKernelError("%s returned %d (%s)" % (name, rc, "argument/setup error" if rc < 0 else "cudaError"))

@@ -1,0 +1,52 @@
+"""Fused clip_grad_norm_(5.) + AdamW over the flat arenas (reference SPMM_models.py:338-343,361-362).
+
+One reduction kernel (sum g^2 over the whole gradient arena) and one update kernel; the clip coefficient, the
+data-parallel 1/world scale and the NaN-guard skip are resolved on the device, so a step issues no host sync.
+Semantics follow torch.optim.AdamW with ONE param group over all parameters (weight decay also on biases,
+LayerNorm and temp, like the reference); the never-used PV word embedding is excluded exactly as torch skips
+parameters whose .grad is None.
+"""
+import torch
+
+from . import kernels as K
+
+
+class FusedClipAdamW(torch.optim.Optimizer):
+    def __init__(self, model, lr=5e-5, weight_decay=0.02, betas=(0.9, 0.999), eps=1e-8, max_norm=5.0):
+        self.A = model.arena()
+        params = [p for p in model.parameters() if p.requires_grad]
+        super().__init__(params, dict(lr=lr, weight_decay=weight_decay, betas=betas, eps=eps))
+        n = self.A.n_total - self.A.adam_start
+        self.exp_avg = torch.zeros(n, device=self.A.device, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(n, device=self.A.device, dtype=torch.float32)
+        self.max_norm = max_norm
+        self.t = 0
+
+    def zero_grad(self, set_to_none=False):
+        self.A.ensure_grads()
+        self.A.zero_grad()
+
+    @torch.no_grad()
+    def step(self, closure=None, skip_flag=None, grad_scale=1.0):
+        A, g0 = self.A, self.A.adam_start
+        grp = self.param_groups[0]
+        self.t += 1
+        K.grad_sumsq(A.G[g0:], A.sumsq)
+        K.adamw(A.P[g0:], A.G[g0:], self.exp_avg, self.exp_avg_sq, grp["lr"], grp["betas"][0], grp["betas"][1], grp["eps"],
+                grp["weight_decay"], self.t, sumsq=A.sumsq, max_norm=self.max_norm, grad_scale=grad_scale,
+                skip_flag=skip_flag)
+
+    def grad_norm(self, grad_scale=1.0):
+        """Total gradient L2 norm of the last step() (device scalar)."""
+        return self.A.sumsq.sqrt() * grad_scale
+
+    def state_dict(self):
+        return {"t": self.t, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        self.t = sd["t"]
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        for g, s in zip(self.param_groups, sd["param_groups"]):
+            g.update(s)

@@ -79,15 +79,15 @@ def value_for(name, shape, momentum_noise=1e-3, salt=0):
 @torch.no_grad()
 def fill_by_name(model, momentum_noise=1e-3, salt=0):
     """Overwrites every parameter / queue of `model` (reference SPMM or ours; same key names)
-    with name-seeded values.  Momentum twins (`*_m.`) get online value + small name-seeded
-    noise so the teacher path is distinguishable from the student path."""
-    sd = model.state_dict()
-    for name, t in sd.items():
+    with name-seeded values through load_state_dict.  Momentum twins (`*_m.`) get online value +
+    small name-seeded noise so the teacher path is distinguishable from the student path."""
+    vals = {}
+    for name, t in model.state_dict().items():
         v = value_for(name, t.shape, momentum_noise, salt)
-        if v is not None:
-            t.copy_(v.to(t.device, t.dtype))
-    if "queue_ptr" in sd:
-        sd["queue_ptr"].zero_()
+        if v is None:
+            v = torch.zeros_like(t) if name == "queue_ptr" else t
+        vals[name] = v.to(t.dtype)
+    model.load_state_dict(vals, strict=True)
     return model
 
 
