@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
 
@@ -226,7 +226,13 @@ def run_ours(args):
     launches = _lib.launch_count()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
-    losses = [float(x) for x in last]
+    losses = [float(x.detach()) for x in last]
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps, "gpu_launches": launches}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # end-to-end through the public API with host batches
     step_e2e()
@@ -331,11 +337,13 @@ def main():
     ap.add_argument("--seq-len", type=int, default=64)
     ap.add_argument("--ragged", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="bare loop for ncu: no e2e / instrumented / CPU legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
-        args.warmup = max(args.warmup, 3)
+        if not args.profile:
+            args.warmup = max(args.warmup, 3)
         run_ours(args)
 
 
