@@ -66,13 +66,14 @@ int spmm_attn_bwd(const void* d_o, int lddo, const void* q, int ldq, const void*
  * y = LN(x) * gamma + beta, optional inverted dropout on y (BertEmbeddings, xbert.py:219).
  * bwd: dx (bf16), atomically accumulates dgamma/dbeta (fp32).  If dx_branch != NULL also writes
  * dx_branch = dx * dropout-mask(branch_seed) (the gradient flowing into `dropout(dense(.))` of
- * xbert.py:371/449) and, if dbias != NULL, accumulates its column sums into dbias (bias grad of that dense). */
+ * xbert.py:371/449) and, if dbias != NULL, accumulates its column sums into dbias (bias grad of that dense).
+ * workspace: >= (8*3*H + 8) floats, zero before first use; the kernel leaves it zeroed (reusable across calls). */
 int spmm_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                        int rows, int H, float eps, float dropout_p, unsigned long long seed, void* stream);
 int spmm_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                        void* dx, float* dgamma, float* dbeta, void* dx_branch, float* dbias, int rows, int H,
                        float out_dropout_p, unsigned long long out_seed, float branch_dropout_p,
-                       unsigned long long branch_seed, void* stream);
+                       unsigned long long branch_seed, float* workspace, void* stream);
 
 /* ------------------------------------------------------------------ embeddings (xbert.py:193-220, SPMM_models.py:82-88)
  * text: x = word[ids] + pos[t] + type[0] (pre-LN sum, bf16).  pv: properties = cat(cls, embed(pv)*(1-m) + mask_tok*m)

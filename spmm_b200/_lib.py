@@ -28,7 +28,7 @@ SIGNATURES = {
     "spmm_attn_bwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32,
                             i32, vp, i32, f32, f32, u64, vp]),
     "spmm_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, f32, f32, u64, vp]),
-    "spmm_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, u64, f32, u64, vp]),
+    "spmm_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, u64, f32, u64, vp, vp]),
     "spmm_embed_text_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "spmm_embed_text_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "spmm_pv_tokens_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),

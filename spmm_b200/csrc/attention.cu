@@ -28,8 +28,9 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 
 // [rows][64] bf16 tile, 16-byte chunks XOR-swizzled by (row & 7)
 __device__ __forceinline__ uint32_t tile64_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
-// [rows][128] bf16 tile
-__device__ __forceinline__ uint32_t tile128_off(int row, int chunk) { return (uint32_t)(row * 256 + ((chunk ^ (row & 7)) << 4)); }
+// [rows][KT] bf16 tile (P / dS): row stride KT*2 bytes
+template <int KT>
+__device__ __forceinline__ uint32_t tileP_off(int row, int chunk) { return (uint32_t)(row * (KT * 2) + ((chunk ^ (row & 7)) << 4)); }
 
 // global [T rows][ld] (head slice of 64 columns) -> swizzled smem tile; rows >= T zero-filled up to rows_pad
 __device__ __forceinline__ void load_tile64(uint8_t* smem, const __nv_bfloat16* g, int ld, int T, int rows_pad) {
@@ -43,8 +44,7 @@ __device__ __forceinline__ void load_tile64(uint8_t* smem, const __nv_bfloat16* 
 
 __device__ __forceinline__ bool attn_keep(unsigned long long seed, int bh, int i, int j, uint32_t thresh16) {
   const unsigned long long e = ((unsigned long long)bh << 14 | (unsigned long long)i << 7 | (unsigned long long)j);
-  const uint32_t h = hash_u32(seed, e >> 1);
-  return ((h >> (16 * (e & 1))) & 0xFFFFu) >= thresh16;
+  return keep16(seed, e, thresh16);
 }
 
 // S[16 x KT] = Q[16 rows of this warp] . K^T for the warp's 16 query rows
@@ -66,15 +66,15 @@ __device__ __forceinline__ void qk_scores(uint32_t sQ, uint32_t sK, int q0, int 
   }
 }
 
-template <int KT>
-__global__ void __launch_bounds__(256)
+template <int QT, int KT>
+__global__ void __launch_bounds__(QT * 2)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
                 const __nv_bfloat16* __restrict__ v, int ldv, __nv_bfloat16* __restrict__ o, int ldo,
                 float* __restrict__ lse, int heads, int Tq, int Tk, const int* __restrict__ kv_len, int causal,
                 int kv_bstride, float scale, unsigned long long seed, uint32_t thresh16, float inv_keep) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* pQ = smem;
-  uint8_t* pK = pQ + 128 * 128;
+  uint8_t* pK = pQ + QT * 128;
   uint8_t* pV = pK + KT * 128;
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,8 +168,8 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat1
 
 // Backward.  Phase 1 (warp = 16 query rows): recompute P, dP = dO V^T, dS = P o (dP - D), dQ = dS K * scale;
 // P (after dropout) and dS are parked in smem as bf16.  Phase 2 (warp = 16 keys): dV = P^T dO, dK = dS^T Q * scale.
-template <int KT>
-__global__ void __launch_bounds__(256)
+template <int QT, int KT>
+__global__ void __launch_bounds__(QT * 2)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ dO, int lddo, const __nv_bfloat16* __restrict__ q, int ldq,
                 const __nv_bfloat16* __restrict__ k, int ldk, const __nv_bfloat16* __restrict__ v, int ldv,
                 const __nv_bfloat16* __restrict__ o, int ldo, const float* __restrict__ lse,
@@ -177,13 +177,14 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ dO, int lddo, const __nv_bfloa
                 __nv_bfloat16* __restrict__ dv, int lddv, int heads, int Tq, int Tk, const int* __restrict__ kv_len,
                 int causal, float scale, unsigned long long seed, uint32_t thresh16, float inv_keep) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* pQ = smem;               // [128][64]
-  uint8_t* pdO = pQ + 128 * 128;    // [128][64]
-  uint8_t* pK = pdO + 128 * 128;    // [KT][64]
+  uint8_t* pQ = smem;               // [QT][64]
+  uint8_t* pdO = pQ + QT * 128;     // [QT][64]
+  uint8_t* pK = pdO + QT * 128;     // [KT][64]
   uint8_t* pV = pK + KT * 128;      // [KT][64]
-  uint8_t* pP = pV + KT * 128;      // [128][128] bf16 (dropped P)
-  uint8_t* pdS = pP + 128 * 256;    // [128][128] bf16
-  float* sD = reinterpret_cast<float*>(pdS + 128 * 256);  // [128]
+  uint8_t* pP = pV + KT * 128;      // [QT][KT] bf16 (dropped P)
+  uint8_t* pdS = pP + QT * KT * 2;  // [QT][KT] bf16
+  float* sD = reinterpret_cast<float*>(pdS + QT * KT * 2);  // [QT]
+  const int nwarps = blockDim.x >> 5;
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tq_pad = (Tq + 15) & ~15;
@@ -193,7 +194,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ dO, int lddo, const __nv_bfloa
   load_tile64(pK, k + krow0 * ldk + h * HD, ldk, Tk, KT);
   load_tile64(pV, v + krow0 * ldv + h * HD, ldv, Tk, KT);
   // D_i = sum_d dO[i,d] * O[i,d]
-  for (int r = warp; r < Tq; r += 8) {
+  for (int r = warp; r < Tq; r += nwarps) {
     float a0, a1, b0, b1;
     unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dO + (qrow0 + r) * lddo + h * HD + 2 * lane), a0, a1);
     unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + (qrow0 + r) * ldo + h * HD + 2 * lane), b0, b1);
@@ -231,8 +232,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ dO, int lddo, const __nv_bfloa
       }
       // park bf16 P / dS: element (row, key) -> tile128 chunk key/8, within-chunk offset (key%8)*2 bytes
       const int key = n * 8 + 2 * t;
-      const uint32_t off0 = tile128_off(i0, key >> 3) + ((key & 7) << 1);
-      const uint32_t off1 = tile128_off(i1, key >> 3) + ((key & 7) << 1);
+      const uint32_t off0 = tileP_off<KT>(i0, key >> 3) + ((key & 7) << 1);
+      const uint32_t off1 = tileP_off<KT>(i1, key >> 3) + ((key & 7) << 1);
       *reinterpret_cast<uint32_t*>(pP + off0) = pack_bf16x2(pd[0], pd[1]);
       *reinterpret_cast<uint32_t*>(pP + off1) = pack_bf16x2(pd[2], pd[3]);
       *reinterpret_cast<uint32_t*>(pdS + off0) = pack_bf16x2(ds[0], ds[1]);
@@ -277,8 +278,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ dO, int lddo, const __nv_bfloa
       // A = P^T / dS^T fragments: stored [q][key]; transposed ldmatrix
       uint32_t p0, p1, p2, p3, e0, e1, e2, e3;
       const int srow = qq + (lane & 7) + ((lane >> 4) << 3), schunk = (k0 >> 3) + ((lane >> 3) & 1);
-      ldsm_x4_t(sP + tile128_off(srow, schunk), p0, p1, p2, p3);
-      ldsm_x4_t(sdS + tile128_off(srow, schunk), e0, e1, e2, e3);
+      ldsm_x4_t(sP + tileP_off<KT>(srow, schunk), p0, p1, p2, p3);
+      ldsm_x4_t(sdS + tileP_off<KT>(srow, schunk), e0, e1, e2, e3);
 #pragma unroll
       for (int np = 0; np < HD / 16; ++np) {
         uint32_t b0, b1, b2, b3;
@@ -326,19 +327,20 @@ extern "C" int spmm_attn_fwd(const void* q, int ldq, const void* k, int ldk, con
   SPMM_ARG((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0 && ((uintptr_t)o & 3) == 0);
   uint32_t th; float ik;
   attn_drop(dropout_p, th, ik);
-  const int KT = Tk <= 64 ? 64 : 128;
-  const size_t smem = 128 * 128 + 2 * (size_t)KT * 128;
+  const int KT = Tk <= 64 ? 64 : 128, QT = Tq <= 64 ? 64 : 128;
   dim3 grid(heads, batch);
   cudaStream_t st = (cudaStream_t)stream;
-#define SPMM_ATTN_FWD(KTV)                                                                                           \
+#define SPMM_ATTN_FWD(QTV, KTV)                                                                                      \
   {                                                                                                                  \
+    constexpr int kSmem = QTV * 128 + 2 * KTV * 128;                                                                 \
     static bool cfg = false;                                                                                         \
-    if (!cfg) { cudaFuncSetAttribute(attn_fwd_kernel<KTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 + 2 * KTV * 128); cfg = true; } \
-    attn_fwd_kernel<KTV><<<grid, 256, smem, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk,        \
+    if (!cfg) { cudaFuncSetAttribute(attn_fwd_kernel<QTV, KTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem); cfg = true; } \
+    attn_fwd_kernel<QTV, KTV><<<grid, QTV * 2, kSmem, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, \
                                                   (const __nv_bfloat16*)v, ldv, (__nv_bfloat16*)o, ldo, lse, heads,  \
                                                   Tq, Tk, kv_len, causal, kv_batch_stride_rows, scale, seed, th, ik); \
   }
-  if (KT == 64) SPMM_ATTN_FWD(64) else SPMM_ATTN_FWD(128)
+  if (QT == 64 && KT == 64) SPMM_ATTN_FWD(64, 64) else if (QT == 64) SPMM_ATTN_FWD(64, 128)
+  else if (KT == 64) SPMM_ATTN_FWD(128, 64) else SPMM_ATTN_FWD(128, 128)
 #undef SPMM_ATTN_FWD
   SPMM_CHECK_LAUNCH();
   return 0;
@@ -356,19 +358,21 @@ extern "C" int spmm_attn_bwd(const void* d_o, int lddo, const void* q, int ldq, 
   uint32_t th; float ik;
   attn_drop(dropout_p, th, ik);
   const int KT = Tk <= 64 ? 64 : 128;
-  const size_t smem = 2 * 128 * 128 + 2 * (size_t)KT * 128 + 2 * 128 * 256 + 128 * sizeof(float);
+  // phase 2 assigns 16 keys per warp, phase 1 16 queries per warp: the CTA needs max(Tq, Tk)/16 warps
+  const int QT = (Tq <= 64 && Tk <= 64) ? 64 : 128;
   dim3 grid(heads, batch);
   cudaStream_t st = (cudaStream_t)stream;
-#define SPMM_ATTN_BWD(KTV)                                                                                            \
+#define SPMM_ATTN_BWD(QTV, KTV)                                                                                       \
   {                                                                                                                   \
+    constexpr int kSmem = 2 * QTV * 128 + 2 * KTV * 128 + 2 * QTV * KTV * 2 + QTV * 4;                                \
     static bool cfg = false;                                                                                          \
-    if (!cfg) { cudaFuncSetAttribute(attn_bwd_kernel<KTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 128 + 2 * KTV * 128 + 2 * 128 * 256 + 512); cfg = true; } \
-    attn_bwd_kernel<KTV><<<grid, 256, smem, st>>>(                                                                    \
+    if (!cfg) { cudaFuncSetAttribute(attn_bwd_kernel<QTV, KTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem); cfg = true; } \
+    attn_bwd_kernel<QTV, KTV><<<grid, QTV * 2, kSmem, st>>>(                                                          \
         (const __nv_bfloat16*)d_o, lddo, (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk,                  \
         (const __nv_bfloat16*)v, ldv, (const __nv_bfloat16*)o, ldo, lse, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, \
         lddk, (__nv_bfloat16*)dv, lddv, heads, Tq, Tk, kv_len, causal, scale, seed, th, ik);                          \
   }
-  if (KT == 64) SPMM_ATTN_BWD(64) else SPMM_ATTN_BWD(128)
+  if (QT == 64) SPMM_ATTN_BWD(64, 64) else if (KT == 64) SPMM_ATTN_BWD(128, 64) else SPMM_ATTN_BWD(128, 128)
 #undef SPMM_ATTN_BWD
   SPMM_CHECK_LAUNCH();
   return 0;

@@ -42,6 +42,7 @@ struct GemmParams {
   uint32_t drop_thresh16;  // keep iff 16-bit draw >= thresh
   float drop_inv_keep;
   uint32_t mn_lbo, mn_sbo;  // MN-major descriptor strides (bytes)
+  int splits, kb_per_split;  // split-K (fp32 accumulate outputs only): partials are reduced with red.global.add
 };
 
 template <int BN>
@@ -50,12 +51,11 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 };
 
 __device__ __forceinline__ bool drop_keep16(unsigned long long seed, unsigned long long e, uint32_t thresh16) {
-  const uint32_t h = hash_u32(seed, e >> 1);
-  return ((h >> (16 * (e & 1))) & 0xFFFFu) >= thresh16;
+  return keep16(seed, e, thresh16);
 }
 
 template <int BN>
@@ -71,11 +71,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + kStages * Cfg::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_mn = num_m * num_n;
+  const int num_tiles = num_mn * p.splits;
+  const int num_kb_total = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -106,8 +108,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % num_m) * BM, n0 = (tile / num_m) * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int mn = tile % num_mn, sp = tile / num_mn;
+      const int m0 = (mn % num_m) * BM, n0 = (mn / num_m) * BN;
+      const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + A_STAGE_BYTES;
@@ -138,7 +142,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int sp = tile / num_mn;
+      const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -149,7 +155,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                         : umma_smem_desc(sa + k * 32, 16, 1024);
           const uint64_t bdesc = p.b_mn ? umma_smem_desc(sb + k * 2048, p.mn_lbo, p.mn_sbo)
                                         : umma_smem_desc(sb + k * 32, 16, 1024);
-          tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+          tc_mma_bf16(d_tmem, adesc, bdesc, idesc, ((kb - kb0) | k) != 0);
         }
         tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -167,12 +173,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const bool do_gelu = p.flags & SPMM_GEMM_GELU, do_dgelu = p.flags & SPMM_GEMM_DGELU;
     const bool do_drop = p.drop_thresh16 != 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % num_m) * BM, n0 = (tile / num_m) * BN;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
+      const int mn = tile % num_mn;
+      const int m0 = (mn % num_m) * BM, n0 = (mn / num_m) * BN;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       const __nv_bfloat16* side = do_dgelu ? p.aux : p.residual;  // at most one bf16 side input per call
       const int lds = do_dgelu ? p.ldaux : p.ldr;
       uint4 side_next[4];
@@ -184,7 +188,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int i = 0; i < 4; ++i) dst[i] = __ldg(sp + i);
         }
       };
+      // While the MMAs of this tile are still running: stage the bias slice in smem, prefetch the first side chunk.
+      if (p.bias != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's s_bias reads are done
+        const int t = threadIdx.x - 128;
+        for (int j = t; j < BN; j += 128) s_bias[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       load_side(0, side_next);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n0 + c * 32;
@@ -196,23 +210,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
-        if (!row_ok) continue;
+        if (row_ok) {
         const bool full_chunk = col0 + 32 <= p.N;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
         if (p.bias != nullptr) {
-          if (full_chunk) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(bp + i);
-              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = *reinterpret_cast<const float4*>(s_bias + c * 32 + 4 * i);   // smem broadcast
+            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
           }
         }
         if (p.pre != nullptr) {
@@ -264,7 +271,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         if (out_f32) {
           float* cp = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
-          if (full_chunk) {
+          if (p.splits > 1) {
+            // split-K partial: vector reduction straight into the fp32 gradient arena
+            if (full_chunk) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + 4 * i), "f"(v[4 * i]),
+                             "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(cp + j, v[j]);
+            }
+          } else if (full_chunk) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -295,6 +314,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               if (col0 + j < p.N) cp[j] = f2bf(v[j]);
           }
         }
+        }  // row_ok
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -347,6 +368,7 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t ou
 static uint32_t g_mn_lbo = 8192, g_mn_sbo = 1024;
 static int g_force_bn = 0;
 static int g_max_ctas = 0;
+static int g_split_k = 1;
 
 template <int BN>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
@@ -358,7 +380,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.splits;
   int ctas = tiles < kNumSMs ? tiles : kNumSMs;
   if (g_max_ctas > 0 && ctas > g_max_ctas) ctas = g_max_ctas;
   gemm_bf16_kernel<BN><<<ctas, 256, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
@@ -385,7 +407,8 @@ using namespace spmm;
 extern "C" int spmm_gemm_debug_config(int mn_lbo_bytes, int mn_sbo_bytes, int force_bn, int max_ctas) {
   if (mn_lbo_bytes > 0) g_mn_lbo = mn_lbo_bytes;
   if (mn_sbo_bytes > 0) g_mn_sbo = mn_sbo_bytes;
-  g_force_bn = force_bn;
+  g_force_bn = force_bn & 0xFFFF;
+  g_split_k = (force_bn & 0x10000) ? 0 : 1;   // bit 16 disables split-K (debug / A-B measurements)
   g_max_ctas = max_ctas;
   return 0;
 }
@@ -425,6 +448,25 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   SPMM_ARG(!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
 
   const int bn = pick_bn(M, N);
+  // split-K for under-filled fp32-accumulate problems (wgrad: few output tiles, very long K)
+  p.splits = 1;
+  const int num_kb = (K + BK - 1) / BK;
+  p.kb_per_split = num_kb;
+  const bool plain_acc = (p.flags == (SPMM_GEMM_OUT_F32 | SPMM_GEMM_ACCUMULATE)) && !p.bias && !p.residual && !p.pre &&
+                         !p.aux && p.drop_thresh16 == 0 && p.alpha == 1.f;
+  if (plain_acc && g_split_k) {
+    const int tiles_mn = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+    int best = 1;
+    double best_eff = (double)tiles_mn / (((tiles_mn + kNumSMs - 1) / kNumSMs) * kNumSMs);
+    for (int sidx = 2; sidx <= 16 && num_kb / sidx >= 4; ++sidx) {
+      const int t = tiles_mn * sidx;
+      const double eff = (double)t / (((t + kNumSMs - 1) / kNumSMs) * kNumSMs);
+      if (eff > best_eff + 0.04) { best_eff = eff; best = sidx; }
+    }
+    p.splits = best;
+    p.kb_per_split = (num_kb + best - 1) / best;
+    p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
+  }
   CUtensorMap ma, mb;
   int rc;
   if (!p.a_mn) rc = make_map(&ma, A, K, M, lda, BK, BM);

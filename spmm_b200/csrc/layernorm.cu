@@ -8,10 +8,10 @@
 namespace spmm {
 
 constexpr int LN_WARPS = 8;
+constexpr int LN_SLOTS = 8;
 
 __device__ __forceinline__ bool ln_keep16(unsigned long long seed, unsigned long long e, uint32_t thresh16) {
-  const uint32_t h = hash_u32(seed, e >> 1);
-  return ((h >> (16 * (e & 1))) & 0xFFFFu) >= thresh16;
+  return keep16(seed, e, thresh16);
 }
 
 template <int NCH>
@@ -85,7 +85,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
               const float* __restrict__ rstd, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
               float* dgamma, float* dbeta, __nv_bfloat16* __restrict__ dx_branch, float* dbias, int rows, int H,
               unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep, unsigned long long br_seed,
-              uint32_t br_thresh, float br_inv_keep) {
+              uint32_t br_thresh, float br_inv_keep, float* ws) {
   extern __shared__ float sh[];  // [LN_WARPS][H]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float pg[NCH][8], pb[NCH][8], ps[NCH][8];
@@ -154,8 +154,11 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
       }
     }
   }
-  // cross-warp reduction of the three column partials, one pass each
+  // Column partials: warps -> smem -> fp32 atomics into one of LN_SLOTS workspace slots (spreads same-address
+  // contention 296-way -> 296/LN_SLOTS-way); the last CTA to finish folds the slots into the gradient arena and
+  // re-zeroes the workspace, so no second launch and no same-address atomic storm on dgamma/dbeta/dbias.
   float* outs[3] = {dgamma, dbeta, dbias};
+  float* slot = ws + (size_t)(blockIdx.x % LN_SLOTS) * 3 * H;
 #pragma unroll
   for (int which = 0; which < 3; ++which) {
     if (outs[which] == nullptr) continue;
@@ -173,8 +176,28 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
       float s = 0.f;
 #pragma unroll
       for (int ww = 0; ww < LN_WARPS; ++ww) s += sh[ww * H + col];
-      atomicAdd(outs[which] + col, s);
+      atomicAdd(slot + which * H + col, s);
     }
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned int s_last;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(ws + (size_t)LN_SLOTS * 3 * H);
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < LN_SLOTS; ++k) {
+        s += __ldcg(ws + (size_t)k * 3 * H + i);
+        ws[(size_t)k * 3 * H + i] = 0.f;
+      }
+      float* o = outs[i / H];
+      if (o != nullptr) o[i % H] += s;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
   }
 }
 
@@ -206,7 +229,8 @@ extern "C" int spmm_layernorm_fwd(const void* x, const float* gamma, const float
 extern "C" int spmm_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                                   const float* gamma, void* dx, float* dgamma, float* dbeta, void* dx_branch,
                                   float* dbias, int rows, int H, float out_dropout_p, unsigned long long out_seed,
-                                  float branch_dropout_p, unsigned long long branch_seed, void* stream) {
+                                  float branch_dropout_p, unsigned long long branch_seed, float* workspace, void* stream) {
+  SPMM_ARG(workspace != nullptr);
   SPMM_ARG(dy && x && mean && rstd && gamma && dx && rows > 0 && H > 0 && H % 8 == 0 && H <= 1024);
   SPMM_ARG((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dx_branch | (uintptr_t)gamma) & 15) == 0);
   uint32_t oth, bth; float oik, bik;
@@ -217,7 +241,7 @@ extern "C" int spmm_layernorm_bwd(const void* dy, const void* x, const float* me
   const int nch = (H + 255) / 256;
   const size_t smem = (size_t)LN_WARPS * H * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-#define SPMM_LN_BWD(N) ln_bwd_kernel<N><<<grid, LN_WARPS * 32, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, dgamma, dbeta, (__nv_bfloat16*)dx_branch, dbias, rows, H, out_seed, oth, oik, branch_seed, bth, bik)
+#define SPMM_LN_BWD(N) ln_bwd_kernel<N><<<grid, LN_WARPS * 32, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, dgamma, dbeta, (__nv_bfloat16*)dx_branch, dbias, rows, H, out_seed, oth, oik, branch_seed, bth, bik, workspace)
   if (nch == 1) SPMM_LN_BWD(1); else if (nch == 2) SPMM_LN_BWD(2); else if (nch == 3) SPMM_LN_BWD(3); else SPMM_LN_BWD(4);
 #undef SPMM_LN_BWD
   SPMM_CHECK_LAUNCH();

@@ -77,8 +77,19 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dbias=None, want_bran
     dxb = torch.empty_like(x) if (want_branch and branch_dropout_p > 0) else None
     call("spmm_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
          dx.data_ptr(), _p(dgamma), _p(dbeta), _p(dxb), _p(dbias), rows, H, float(out_dropout_p), int(out_seed),
-         float(branch_dropout_p), int(branch_seed), _st())
+         float(branch_dropout_p), int(branch_seed), _ln_workspace(x.device).data_ptr(), _st())
     return dx, (dxb if dxb is not None else dx)
+
+
+_LN_WS = {}
+
+
+def _ln_workspace(device):
+    """Persistent zeroed scratch for the LayerNorm-backward column reduction (the kernel re-zeroes it)."""
+    ws = _LN_WS.get(device)
+    if ws is None:
+        ws = _LN_WS[device] = torch.zeros(8 * 3 * 1024 + 8, device=device, dtype=torch.float32)
+    return ws
 
 
 def ema(p, p_m, p_bf16, p_m_bf16, momentum):
