@@ -42,6 +42,7 @@ struct GemmParams {
   uint32_t drop_thresh16;  // keep iff 16-bit draw >= thresh
   float drop_inv_keep;
   uint32_t mn_lbo, mn_sbo;  // MN-major descriptor strides (bytes)
+  int debug_nomma;           // debug: consume stages without issuing MMAs (TMA ingest measurement)
   int splits, kb_per_split;  // split-K (fp32 accumulate outputs only): partials are reduced with red.global.add
 };
 
@@ -58,6 +59,159 @@ __device__ __forceinline__ bool drop_keep16(unsigned long long seed, unsigned lo
   return keep16(seed, e, thresh16);
 }
 
+// One 128 x BN accumulator tile: TMEM -> registers -> fused epilogue -> global.  Called by the 4 epilogue warps
+// (threads 128..255); `q` is the TMEM lane quadrant of the calling warp.  Shared by the 1-CTA and 2-CTA kernels.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const int m0, const int n0, const uint32_t tmem_base,
+                                              const int acc, const int q, const int lane, float* s_bias,
+                                              uint64_t* tfull, const uint32_t acc_phase) {
+  const bool out_f32 = p.flags & SPMM_GEMM_OUT_F32, accum = p.flags & SPMM_GEMM_ACCUMULATE;
+  const bool do_gelu = p.flags & SPMM_GEMM_GELU, do_dgelu = p.flags & SPMM_GEMM_DGELU;
+  const bool do_drop = p.drop_thresh16 != 0;
+  const int row = m0 + q * 32 + lane;
+  const bool row_ok = row < p.M;
+  const __nv_bfloat16* side = do_dgelu ? p.aux : p.residual;  // at most one bf16 side input per call
+  const int lds = do_dgelu ? p.ldaux : p.ldr;
+  uint4 side_next[4];
+  auto load_side = [&](int c, uint4(&dst)[4]) {
+    const int col0 = n0 + c * 32;
+    if (side != nullptr && row_ok && col0 + 32 <= p.N) {
+      const uint4* sp = reinterpret_cast<const uint4*>(side + (size_t)row * lds + col0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = __ldg(sp + i);
+    }
+  };
+  // While the MMAs of this tile are still running: stage the bias slice in smem, prefetch the first side chunk.
+  if (p.bias != nullptr) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's s_bias reads are done
+    const int t = threadIdx.x - 128;
+    for (int j = t; j < BN; j += 128) s_bias[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+  load_side(0, side_next);
+  mbar_wait(tfull, acc_phase);
+  tc_fence_after();
+  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= p.N) break;  // warp-uniform
+    uint4 side_cur[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) side_cur[i] = side_next[i];
+    if (c + 1 < BN / 32) load_side(c + 1, side_next);
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    tmem_ld_wait();
+    if (row_ok) {
+    const bool full_chunk = col0 + 32 <= p.N;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = *reinterpret_cast<const float4*>(s_bias + c * 32 + 4 * i);   // smem broadcast
+        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    }
+    if (p.pre != nullptr) {
+      __nv_bfloat16* pp = p.pre + (size_t)row * p.ldp + col0;
+      if (full_chunk) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+          o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+          reinterpret_cast<uint4*>(pp)[i] = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) pp[j] = f2bf(v[j]);
+      }
+    }
+    if (do_gelu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    }
+    if (do_drop) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const unsigned long long e = (unsigned long long)row * (unsigned long long)p.N + (col0 + j);
+        v[j] = drop_keep16(p.drop_seed, e, p.drop_thresh16) ? v[j] * p.drop_inv_keep : 0.f;
+      }
+    }
+    if (side != nullptr) {
+      float s[32];
+      if (full_chunk) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          unpack_bf16x2(side_cur[i].x, s[8 * i], s[8 * i + 1]); unpack_bf16x2(side_cur[i].y, s[8 * i + 2], s[8 * i + 3]);
+          unpack_bf16x2(side_cur[i].z, s[8 * i + 4], s[8 * i + 5]); unpack_bf16x2(side_cur[i].w, s[8 * i + 6], s[8 * i + 7]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s[j] = (col0 + j < p.N) ? bf2f(side[(size_t)row * lds + col0 + j]) : 0.f;
+      }
+      if (do_dgelu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= dgelu_erf(s[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += s[j];
+      }
+    }
+    if (out_f32) {
+      float* cp = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+      if (p.splits > 1) {
+        // split-K partial: vector reduction straight into the fp32 gradient arena
+        if (full_chunk) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + 4 * i), "f"(v[4 * i]),
+                         "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) atomicAdd(cp + j, v[j]);
+        }
+      } else if (full_chunk) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          if (accum) {
+            const float4 old = reinterpret_cast<float4*>(cp)[i];
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          reinterpret_cast<float4*>(cp)[i] = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) cp[j] = accum ? cp[j] + v[j] : v[j];
+      }
+    } else {
+      __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
+      if (full_chunk) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+          o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+          reinterpret_cast<uint4*>(cp)[i] = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) cp[j] = f2bf(v[j]);
+      }
+    }
+    }  // row_ok
+    __syncwarp();
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -65,7 +219,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for SWIZZLE_128B, computed on the shared-space offset so accesses stay LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
@@ -147,6 +302,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (p.debug_nomma) {
+          mbar_arrive(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
         const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
@@ -160,7 +320,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      if (p.debug_nomma) mbar_arrive(&tfull_bar[acc]);
+      else tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -169,154 +330,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool out_f32 = p.flags & SPMM_GEMM_OUT_F32, accum = p.flags & SPMM_GEMM_ACCUMULATE;
-    const bool do_gelu = p.flags & SPMM_GEMM_GELU, do_dgelu = p.flags & SPMM_GEMM_DGELU;
-    const bool do_drop = p.drop_thresh16 != 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mn = tile % num_mn;
       const int m0 = (mn % num_m) * BM, n0 = (mn / num_m) * BN;
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const __nv_bfloat16* side = do_dgelu ? p.aux : p.residual;  // at most one bf16 side input per call
-      const int lds = do_dgelu ? p.ldaux : p.ldr;
-      uint4 side_next[4];
-      auto load_side = [&](int c, uint4(&dst)[4]) {
-        const int col0 = n0 + c * 32;
-        if (side != nullptr && row_ok && col0 + 32 <= p.N) {
-          const uint4* sp = reinterpret_cast<const uint4*>(side + (size_t)row * lds + col0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = __ldg(sp + i);
-        }
-      };
-      // While the MMAs of this tile are still running: stage the bias slice in smem, prefetch the first side chunk.
-      if (p.bias != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's s_bias reads are done
-        const int t = threadIdx.x - 128;
-        for (int j = t; j < BN; j += 128) s_bias[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-      load_side(0, side_next);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint4 side_cur[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) side_cur[i] = side_next[i];
-        if (c + 1 < BN / 32) load_side(c + 1, side_next);
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        if (row_ok) {
-        const bool full_chunk = col0 + 32 <= p.N;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b = *reinterpret_cast<const float4*>(s_bias + c * 32 + 4 * i);   // smem broadcast
-            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-          }
-        }
-        if (p.pre != nullptr) {
-          __nv_bfloat16* pp = p.pre + (size_t)row * p.ldp + col0;
-          if (full_chunk) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-              o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-              reinterpret_cast<uint4*>(pp)[i] = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) pp[j] = f2bf(v[j]);
-          }
-        }
-        if (do_gelu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (do_drop) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const unsigned long long e = (unsigned long long)row * (unsigned long long)p.N + (col0 + j);
-            v[j] = drop_keep16(p.drop_seed, e, p.drop_thresh16) ? v[j] * p.drop_inv_keep : 0.f;
-          }
-        }
-        if (side != nullptr) {
-          float s[32];
-          if (full_chunk) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              unpack_bf16x2(side_cur[i].x, s[8 * i], s[8 * i + 1]); unpack_bf16x2(side_cur[i].y, s[8 * i + 2], s[8 * i + 3]);
-              unpack_bf16x2(side_cur[i].z, s[8 * i + 4], s[8 * i + 5]); unpack_bf16x2(side_cur[i].w, s[8 * i + 6], s[8 * i + 7]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s[j] = (col0 + j < p.N) ? bf2f(side[(size_t)row * lds + col0 + j]) : 0.f;
-          }
-          if (do_dgelu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= dgelu_erf(s[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += s[j];
-          }
-        }
-        if (out_f32) {
-          float* cp = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
-          if (p.splits > 1) {
-            // split-K partial: vector reduction straight into the fp32 gradient arena
-            if (full_chunk) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + 4 * i), "f"(v[4 * i]),
-                             "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) atomicAdd(cp + j, v[j]);
-            }
-          } else if (full_chunk) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-              if (accum) {
-                const float4 old = reinterpret_cast<float4*>(cp)[i];
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-              }
-              reinterpret_cast<float4*>(cp)[i] = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) cp[j] = accum ? cp[j] + v[j] : v[j];
-          }
-        } else {
-          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
-          if (full_chunk) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-              o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-              reinterpret_cast<uint4*>(cp)[i] = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) cp[j] = f2bf(v[j]);
-          }
-        }
-        }  // row_ok
-        __syncwarp();
-      }
+      epilogue_tile<BN>(p, m0, n0, tmem_base, acc, q, lane, s_bias, &tfull_bar[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -329,6 +346,198 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ 2-CTA kernel
+// CTA pair (cluster of 2, same TPC) computes a 256 x 256 tile with tcgen05.mma.cta_group::2: each CTA stages its
+// own 128 rows of A and its own 128 columns of B (32 KB per 64-deep k-block instead of 48 KB), the leader CTA issues
+// UMMA M=256 that reads both CTAs' shared memory, and each CTA's TMEM receives its 128 output rows.  The mainloop of
+// the 1-CTA kernel is bound by L2->SM ingest (~48 B/cycle/SM measured); this halves the B traffic per FLOP.
+constexpr int BN2 = 256;
+constexpr int B2_STAGE_BYTES = (BN2 / 2) * BK * 2;               // this CTA's half of the B tile
+constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;     // 32 KB
+constexpr int kStages2 = 6;
+constexpr int SMEM2_BYTES = kStages2 * STAGE2_BYTES + 1024 + 256 + BN2 * 4;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1) {
+  // the mbarrier lives in the leader CTA (peer bit of the shared::cluster address cleared)
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {  // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // remote arrive on the leader CTA's copy
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages2 * STAGE2_BYTES);
+  uint64_t* empty_bar = full_bar + kStages2;
+  uint64_t* tfull_bar = empty_bar + kStages2;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + kStages2 * STAGE2_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_m = (p.M + 2 * BM - 1) / (2 * BM), num_n = (p.N + BN2 - 1) / BN2;
+  const int num_mn = num_m * num_n;
+  const int num_tiles = num_mn * p.splits;
+  const int num_kb_total = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(&full_bar[s], 1);    // leader's copy is the one in use: 1 arrive (leader producer) + tx of both CTAs
+      mbar_init(&empty_bar[s], 1);   // multicast commit from the leader's MMA thread
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);   // multicast commit
+      mbar_init(&tempty_bar[s], 8);  // leader's copy: 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // peer barriers initialised / TMEM allocated before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int mn = tile % num_mn, sp = tile / num_mn;
+      const int m0 = (mn % num_m) * 2 * BM + (int)rank * BM;
+      const int nb0 = (mn / num_m) * BN2 + (int)rank * (BN2 / 2);
+      const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * STAGE2_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+        if (p.a_mn == 0) {
+          tma_load_2d_2sm(sa, &map_a, &full_bar[stage], kb * BK, m0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BM / 64; ++c) tma_load_2d_2sm(sa + c * 8192, &map_a, &full_bar[stage], m0 + c * 64, kb * BK);
+        }
+        if (p.b_mn == 0) {
+          tma_load_2d_2sm(sb, &map_b, &full_bar[stage], kb * BK, nb0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN2 / 128; ++c) tma_load_2d_2sm(sb + c * 8192, &map_b, &full_bar[stage], nb0 + c * 64, kb * BK);
+        }
+        if (++stage == kStages2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    const uint32_t idesc = umma_idesc_bf16(2 * BM, BN2, p.a_mn, p.b_mn);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN2;
+      const int sp = tile / num_mn;
+      const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (p.debug_nomma) {
+          mbar_arrive_rank(&empty_bar[stage], 0);
+          mbar_arrive_rank(&empty_bar[stage], 1);
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+          continue;
+        }
+        const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
+        const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t adesc = p.a_mn ? umma_smem_desc(sa + k * 2048, p.mn_lbo, p.mn_sbo)
+                                        : umma_smem_desc(sa + k * 32, 16, 1024);
+          const uint64_t bdesc = p.b_mn ? umma_smem_desc(sb + k * 2048, p.mn_lbo, p.mn_sbo)
+                                        : umma_smem_desc(sb + k * 32, 16, 1024);
+          tc_mma_bf16_2sm(d_tmem, adesc, bdesc, idesc, ((kb - kb0) | k) != 0);
+        }
+        tc_commit_2sm(&empty_bar[stage]);   // both CTAs' producers may refill this slot
+        if (++stage == kStages2) { stage = 0; phase ^= 1; }
+      }
+      if (p.debug_nomma) { mbar_arrive_rank(&tfull_bar[acc], 0); mbar_arrive_rank(&tfull_bar[acc], 1); }
+      else tc_commit_2sm(&tfull_bar[acc]);  // both CTAs' epilogues
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs: own 128 rows x 256 columns) =====================
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int mn = tile % num_mn;
+      const int m0 = (mn % num_m) * 2 * BM + (int)rank * BM, n0 = (mn / num_m) * BN2;
+      epilogue_tile<BN2>(p, m0, n0, tmem_base, acc, q, lane, s_bias, &tfull_bar[acc], acc_phase);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the leader's MMAs read this CTA's smem and signal its barriers: leave together
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -369,6 +578,7 @@ static uint32_t g_mn_lbo = 8192, g_mn_sbo = 1024;
 static int g_force_bn = 0;
 static int g_max_ctas = 0;
 static int g_split_k = 1;
+static int g_nomma = 0;
 
 template <int BN>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
@@ -384,6 +594,23 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
   int ctas = tiles < kNumSMs ? tiles : kNumSMs;
   if (g_max_ctas > 0 && ctas > g_max_ctas) ctas = g_max_ctas;
   gemm_bf16_kernel<BN><<<ctas, 256, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+static int g_use_2cta = 1;
+
+static int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN2 - 1) / BN2) * p.splits;
+  int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+  if (g_max_ctas > 0 && 2 * pairs > g_max_ctas) pairs = g_max_ctas / 2 > 0 ? g_max_ctas / 2 : 1;
+  gemm2_bf16_kernel<<<2 * pairs, 256, SMEM2_BYTES, st>>>(ma, mb, p);
   SPMM_CHECK_LAUNCH();
   return 0;
 }
@@ -409,6 +636,8 @@ extern "C" int spmm_gemm_debug_config(int mn_lbo_bytes, int mn_sbo_bytes, int fo
   if (mn_sbo_bytes > 0) g_mn_sbo = mn_sbo_bytes;
   g_force_bn = force_bn & 0xFFFF;
   g_split_k = (force_bn & 0x10000) ? 0 : 1;   // bit 16 disables split-K (debug / A-B measurements)
+  g_use_2cta = (force_bn & 0x40000) ? 0 : 1;  // bit 18 disables the 2-CTA kernel
+  g_nomma = (force_bn & 0x20000) ? 1 : 0;     // bit 17: skip MMAs (TMA-only pipeline timing; results are garbage)
   g_max_ctas = max_ctas;
   return 0;
 }
@@ -425,6 +654,7 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   p.C = C; p.ldc = ldc;
   p.alpha = 1.f;
   p.mn_lbo = g_mn_lbo; p.mn_sbo = g_mn_sbo;
+  p.debug_nomma = g_nomma;
   if (epi) {
     p.bias = epi->bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(epi->residual); p.ldr = epi->ld_residual;
@@ -447,7 +677,10 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   SPMM_ARG(!p.pre || p.ldp % 8 == 0);
   SPMM_ARG(!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
 
-  const int bn = pick_bn(M, N);
+  const bool use2 = g_use_2cta && !g_force_bn && M > BM && N > 128;   // 2-CTA 256x256 pair tiles
+  const int bn = use2 ? BN2 : pick_bn(M, N);
+  const int slots = use2 ? kNumSMs / 2 : kNumSMs;
+  const int tiles_mn = use2 ? ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2) : ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
   // split-K for under-filled fp32-accumulate problems (wgrad: few output tiles, very long K)
   p.splits = 1;
   const int num_kb = (K + BK - 1) / BK;
@@ -455,12 +688,11 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   const bool plain_acc = (p.flags == (SPMM_GEMM_OUT_F32 | SPMM_GEMM_ACCUMULATE)) && !p.bias && !p.residual && !p.pre &&
                          !p.aux && p.drop_thresh16 == 0 && p.alpha == 1.f;
   if (plain_acc && g_split_k) {
-    const int tiles_mn = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
     int best = 1;
-    double best_eff = (double)tiles_mn / (((tiles_mn + kNumSMs - 1) / kNumSMs) * kNumSMs);
+    double best_eff = (double)tiles_mn / (((tiles_mn + slots - 1) / slots) * slots);
     for (int sidx = 2; sidx <= 16 && num_kb / sidx >= 4; ++sidx) {
       const int t = tiles_mn * sidx;
-      const double eff = (double)t / (((t + kNumSMs - 1) / kNumSMs) * kNumSMs);
+      const double eff = (double)t / (((t + slots - 1) / slots) * slots);
       if (eff > best_eff + 0.04) { best_eff = eff; best = sidx; }
     }
     p.splits = best;
@@ -472,9 +704,10 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   if (!p.a_mn) rc = make_map(&ma, A, K, M, lda, BK, BM);
   else rc = make_map(&ma, A, M, K, lda, 64, BK);
   if (rc) return rc;
-  if (!p.b_mn) rc = make_map(&mb, B, K, N, ldb, BK, bn);
+  if (!p.b_mn) rc = make_map(&mb, B, K, N, ldb, BK, use2 ? BN2 / 2 : bn);
   else rc = make_map(&mb, B, N, K, ldb, 64, BK);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (use2) return launch2(ma, mb, p, st);
   return bn == 256 ? launch<256>(ma, mb, p, st) : launch<128>(ma, mb, p, st);
 }

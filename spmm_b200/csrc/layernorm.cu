@@ -1,17 +1,29 @@
 // LayerNorm forward/backward over bf16 rows (reference: nn.LayerNorm sites xbert.py:184,366,444,670;
 // eps 1e-12; fp32 statistics as torch's autocast keeps LayerNorm in fp32).
-// One warp per row; a lane owns 16-byte chunks {lane, lane+32, ...} of the row, so a 768-wide row is
-// three fully coalesced 512-byte warp transactions.  HBM-bound: 2 B read + 2 B write per element forward.
+// Forward / backward-dx: one warp per row; a lane owns 16-byte chunks {lane, lane+32, ...} of the row, so a 768-wide
+// row is three fully coalesced 512-byte warp transactions.  Backward parameter gradients (dgamma, dbeta and the bias
+// gradient of the dense that feeds the residual branch) are a separate column-parallel reduction kernel.
+// HBM-bound: 4 B/element forward, 6-8 B/element for dx, 6 B/element for the parameter reduction.
 #include "common.cuh"
 #include "spmm_b200.h"
 
 namespace spmm {
 
 constexpr int LN_WARPS = 8;
-constexpr int LN_SLOTS = 8;
 
-__device__ __forceinline__ bool ln_keep16(unsigned long long seed, unsigned long long e, uint32_t thresh16) {
-  return keep16(seed, e, thresh16);
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  unpack_bf16x2(u.x, v[0], v[1]); unpack_bf16x2(u.y, v[2], v[3]);
+  unpack_bf16x2(u.z, v[4], v[5]); unpack_bf16x2(u.w, v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&o)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
 template <int NCH>
@@ -29,9 +41,7 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
   for (int c = 0; c < NCH; ++c) {
     const int col = (lane + 32 * c) * 8;
     if (col < H) {
-      const uint4 u = *reinterpret_cast<const uint4*>(xr + col);
-      unpack_bf16x2(u.x, v[c][0], v[c][1]); unpack_bf16x2(u.y, v[c][2], v[c][3]);
-      unpack_bf16x2(u.z, v[c][4], v[c][5]); unpack_bf16x2(u.w, v[c][6], v[c][7]);
+      load8(xr + col, v[c]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) sum += v[c][j];
     } else {
@@ -59,145 +69,124 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
   for (int c = 0; c < NCH; ++c) {
     const int col = (lane + 32 * c) * 8;
     if (col < H) {
-      const float4 g0 = *reinterpret_cast<const float4*>(gamma + col), g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(beta + col), b1 = *reinterpret_cast<const float4*>(beta + col + 4);
-      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o[8];
+      float g[8], b[8], o[8];
+      load8f(gamma + col, g);
+      load8f(beta + col, b);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         o[j] = (v[c][j] - mean) * rstd * g[j] + b[j];
-        if (thresh16) o[j] = ln_keep16(seed, (unsigned long long)row * H + col + j, thresh16) ? o[j] * inv_keep : 0.f;
+        if (thresh16) o[j] = keep16(seed, (unsigned long long)row * H + col + j, thresh16) ? o[j] * inv_keep : 0.f;
       }
-      uint4 u;
-      u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-      *reinterpret_cast<uint4*>(yr + col) = u;
+      store8(yr + col, o);
     }
   }
 }
 
-// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma; dgamma += dy * xhat; dbeta += dy.
-// A CTA walks rows blockIdx.x, +gridDim.x, ... keeping per-lane column partials in registers, then reduces the
-// 8 warps through shared memory and issues one fp32 atomicAdd per column per CTA.
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma; optionally dx_branch = dx * dropout mask.
 template <int NCH>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
-              const float* __restrict__ rstd, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
-              float* dgamma, float* dbeta, __nv_bfloat16* __restrict__ dx_branch, float* dbias, int rows, int H,
-              unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep, unsigned long long br_seed,
-              uint32_t br_thresh, float br_inv_keep, float* ws) {
-  extern __shared__ float sh[];  // [LN_WARPS][H]
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float pg[NCH][8], pb[NCH][8], ps[NCH][8];
+ln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                 const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                 __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_branch, int rows, int H,
+                 unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep, unsigned long long br_seed,
+                 uint32_t br_thresh, float br_inv_keep) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float mu = mean[row], rs = rstd[row];
+  float xh[NCH][8], g[NCH][8];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int c = 0; c < NCH; ++c)
+  for (int c = 0; c < NCH; ++c) {
+    const int col = (lane + 32 * c) * 8;
+    if (col < H) {
+      float d[8], gm[8];
+      load8(x + (size_t)row * H + col, xh[c]);
+      load8(dy + (size_t)row * H + col, d);
+      load8f(gamma + col, gm);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) pg[c][j] = pb[c][j] = ps[c][j] = 0.f;
+      for (int j = 0; j < 8; ++j) {
+        if (out_thresh)  // forward applied dropout after the affine: dy_affine = dy * mask / keep
+          d[j] = keep16(out_seed, (unsigned long long)row * H + col + j, out_thresh) ? d[j] * out_inv_keep : 0.f;
+        xh[c][j] = (xh[c][j] - mu) * rs;
+        g[c][j] = d[j] * gm[j];
+        s1 += g[c][j];
+        s2 += g[c][j] * xh[c][j];
+      }
+    }
+  }
+  s1 = warp_sum(s1) / H;
+  s2 = warp_sum(s2) / H;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = (lane + 32 * c) * 8;
+    if (col < H) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rs * (g[c][j] - s1 - xh[c][j] * s2);
+      store8(dx + (size_t)row * H + col, o);
+      if (dx_branch) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = keep16(br_seed, (unsigned long long)row * H + col + j, br_thresh) ? o[j] * br_inv_keep : 0.f;
+        store8(dx_branch + (size_t)row * H + col, o);
+      }
+    }
+  }
+}
 
-  for (int row = blockIdx.x * LN_WARPS + w; row < rows; row += gridDim.x * LN_WARPS) {
-    const float mu = mean[row], rs = rstd[row];
-    float xh[NCH][8], g[NCH][8];
-    float s1 = 0.f, s2 = 0.f;
+// Column-parallel parameter gradients: dgamma[c] += sum_r dy*xhat, dbeta[c] += sum_r dy, dbias[c] += sum_r branch[r][c].
+// block = 32 lanes (8 columns each = 256 columns) x 8 warps striding rows; grid = (ceil(H/256), row blocks).
+__global__ void __launch_bounds__(256)
+ln_bwd_param_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const __nv_bfloat16* __restrict__ branch, float* dgamma, float* dbeta, float* dbias, int rows, int H,
+                    int rows_per_block, unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep) {
+  __shared__ float sh[3][8][33 * 8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float ag[8], ab[8], as[8];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int col = (lane + 32 * c) * 8;
-      if (col < H) {
-        const uint4 ux = *reinterpret_cast<const uint4*>(x + (size_t)row * H + col);
-        const uint4 ud = *reinterpret_cast<const uint4*>(dy + (size_t)row * H + col);
-        float d[8];
-        unpack_bf16x2(ux.x, xh[c][0], xh[c][1]); unpack_bf16x2(ux.y, xh[c][2], xh[c][3]);
-        unpack_bf16x2(ux.z, xh[c][4], xh[c][5]); unpack_bf16x2(ux.w, xh[c][6], xh[c][7]);
-        unpack_bf16x2(ud.x, d[0], d[1]); unpack_bf16x2(ud.y, d[2], d[3]);
-        unpack_bf16x2(ud.z, d[4], d[5]); unpack_bf16x2(ud.w, d[6], d[7]);
-        const float4 g0 = *reinterpret_cast<const float4*>(gamma + col), g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  for (int j = 0; j < 8; ++j) ag[j] = ab[j] = as[j] = 0.f;
+  if (c0 < H) {
+    for (int r = r0 + w; r < r1; r += 8) {
+      float d[8], xv[8];
+      load8(dy + (size_t)r * H + c0, d);
+      load8(x + (size_t)r * H + c0, xv);
+      const float mu = mean[r], rs = rstd[r];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (out_thresh)  // forward applied dropout after the affine: dy_affine = dy * mask / keep
-            d[j] = ln_keep16(out_seed, (unsigned long long)row * H + col + j, out_thresh) ? d[j] * out_inv_keep : 0.f;
-          xh[c][j] = (xh[c][j] - mu) * rs;
-          g[c][j] = d[j] * gm[j];
-          s1 += g[c][j];
-          s2 += g[c][j] * xh[c][j];
-          pg[c][j] += d[j] * xh[c][j];
-          pb[c][j] += d[j];
-        }
+      for (int j = 0; j < 8; ++j) {
+        if (out_thresh)
+          d[j] = keep16(out_seed, (unsigned long long)r * H + c0 + j, out_thresh) ? d[j] * out_inv_keep : 0.f;
+        ag[j] += d[j] * (xv[j] - mu) * rs;
+        ab[j] += d[j];
       }
-    }
-    s1 = warp_sum(s1) / H;
-    s2 = warp_sum(s2) / H;
+      if (dbias != nullptr) {
+        float bv[8];
+        load8(branch + (size_t)r * H + c0, bv);
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int col = (lane + 32 * c) * 8;
-      if (col < H) {
-        float o[8], ob[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          o[j] = rs * (g[c][j] - s1 - xh[c][j] * s2);
-          ob[j] = o[j];
-          if (br_thresh)
-            ob[j] = ln_keep16(br_seed, (unsigned long long)row * H + col + j, br_thresh) ? o[j] * br_inv_keep : 0.f;
-        }
-        uint4 u;
-        u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-        *reinterpret_cast<uint4*>(dx + (size_t)row * H + col) = u;
-        if (dx_branch) {
-          uint4 ub;
-          ub.x = pack_bf16x2(ob[0], ob[1]); ub.y = pack_bf16x2(ob[2], ob[3]); ub.z = pack_bf16x2(ob[4], ob[5]); ub.w = pack_bf16x2(ob[6], ob[7]);
-          *reinterpret_cast<uint4*>(dx_branch + (size_t)row * H + col) = ub;
-        }
-        if (dbias) {
-          // bias grad of the preceding dense = column sums of what flows into it (bf16-rounded like the wgrad operand)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ps[c][j] += bf2f(f2bf(ob[j]));
-        }
+        for (int j = 0; j < 8; ++j) as[j] += bv[j];
       }
     }
   }
-  // Column partials: warps -> smem -> fp32 atomics into one of LN_SLOTS workspace slots (spreads same-address
-  // contention 296-way -> 296/LN_SLOTS-way); the last CTA to finish folds the slots into the gradient arena and
-  // re-zeroes the workspace, so no second launch and no same-address atomic storm on dgamma/dbeta/dbias.
-  float* outs[3] = {dgamma, dbeta, dbias};
-  float* slot = ws + (size_t)(blockIdx.x % LN_SLOTS) * 3 * H;
 #pragma unroll
-  for (int which = 0; which < 3; ++which) {
-    if (outs[which] == nullptr) continue;
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int col = (lane + 32 * c) * 8;
-      if (col < H) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sh[w * H + col + j] = which == 0 ? pg[c][j] : (which == 1 ? pb[c][j] : ps[c][j]);
-      }
-    }
-    __syncthreads();
-    for (int col = threadIdx.x; col < H; col += blockDim.x) {
-      float s = 0.f;
-#pragma unroll
-      for (int ww = 0; ww < LN_WARPS; ++ww) s += sh[ww * H + col];
-      atomicAdd(slot + which * H + col, s);
-    }
+  for (int j = 0; j < 8; ++j) {
+    sh[0][w][lane * 8 + j + lane / 4] = ag[j];
+    sh[1][w][lane * 8 + j + lane / 4] = ab[j];
+    sh[2][w][lane * 8 + j + lane / 4] = as[j];
   }
-  __threadfence();
   __syncthreads();
-  __shared__ unsigned int s_last;
-  unsigned int* counter = reinterpret_cast<unsigned int*>(ws + (size_t)LN_SLOTS * 3 * H);
-  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) {
-      float s = 0.f;
+  // 256 threads: thread t reduces column t of this slab for the three outputs
+  const int t = threadIdx.x, col = blockIdx.x * 256 + t;
+  if (col < H) {
+    const int idx = t + (t / 8) / 4;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int k = 0; k < LN_SLOTS; ++k) {
-        s += __ldcg(ws + (size_t)k * 3 * H + i);
-        ws[(size_t)k * 3 * H + i] = 0.f;
-      }
-      float* o = outs[i / H];
-      if (o != nullptr) o[i % H] += s;
-    }
-    if (threadIdx.x == 0) *counter = 0u;
+    for (int ww = 0; ww < 8; ++ww) { s0 += sh[0][ww][idx]; s1 += sh[1][ww][idx]; s2 += sh[2][ww][idx]; }
+    if (dgamma) atomicAdd(dgamma + col, s0);
+    if (dbeta) atomicAdd(dbeta + col, s1);
+    if (dbias) atomicAdd(dbias + col, s2);
   }
 }
 
@@ -229,21 +218,33 @@ extern "C" int spmm_layernorm_fwd(const void* x, const float* gamma, const float
 extern "C" int spmm_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                                   const float* gamma, void* dx, float* dgamma, float* dbeta, void* dx_branch,
                                   float* dbias, int rows, int H, float out_dropout_p, unsigned long long out_seed,
-                                  float branch_dropout_p, unsigned long long branch_seed, float* workspace, void* stream) {
-  SPMM_ARG(workspace != nullptr);
+                                  float branch_dropout_p, unsigned long long branch_seed, float* workspace,
+                                  void* stream) {
+  (void)workspace;  // kept in the ABI for callers that pre-allocate scratch; the two-kernel scheme needs none
   SPMM_ARG(dy && x && mean && rstd && gamma && dx && rows > 0 && H > 0 && H % 8 == 0 && H <= 1024);
   SPMM_ARG((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dx_branch | (uintptr_t)gamma) & 15) == 0);
+  SPMM_ARG(!(dx_branch != nullptr && branch_dropout_p <= 0.f));
   uint32_t oth, bth; float oik, bik;
   drop_params(out_dropout_p, oth, oik);
   drop_params(branch_dropout_p, bth, bik);
-  int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-  if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+  const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   const int nch = (H + 255) / 256;
-  const size_t smem = (size_t)LN_WARPS * H * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-#define SPMM_LN_BWD(N) ln_bwd_kernel<N><<<grid, LN_WARPS * 32, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, dgamma, dbeta, (__nv_bfloat16*)dx_branch, dbias, rows, H, out_seed, oth, oik, branch_seed, bth, bik, workspace)
+#define SPMM_LN_BWD(N) ln_bwd_dx_kernel<N><<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_branch, rows, H, out_seed, oth, oik, branch_seed, bth, bik)
   if (nch == 1) SPMM_LN_BWD(1); else if (nch == 2) SPMM_LN_BWD(2); else if (nch == 3) SPMM_LN_BWD(3); else SPMM_LN_BWD(4);
 #undef SPMM_LN_BWD
   SPMM_CHECK_LAUNCH();
+  if (dgamma || dbeta || dbias) {
+    const int col_blocks = (H + 255) / 256;
+    int row_blocks = (2 * kNumSMs + col_blocks - 1) / col_blocks;
+    if (row_blocks > (rows + 31) / 32) row_blocks = (rows + 31) / 32;
+    if (row_blocks < 1) row_blocks = 1;
+    const int rpb = (rows + row_blocks - 1) / row_blocks;
+    const __nv_bfloat16* branch = (const __nv_bfloat16*)(dx_branch ? dx_branch : dx);
+    ln_bwd_param_kernel<<<dim3(col_blocks, row_blocks), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                                                                     mean, rstd, branch, dgamma, dbeta, dbias, rows, H, rpb,
+                                                                     out_seed, oth, oik);
+    SPMM_CHECK_LAUNCH();
+  }
   return 0;
 }
