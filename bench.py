@@ -201,14 +201,33 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
+    graphed = None if args.eager else trainer.GraphedTrainStep(model, opt)
+
+    def step_eager():
         return trainer.train_step(model, opt, pv, ids, mask, alpha)
 
-    def step_e2e():
-        a, b, c = pv_h.to(dev, non_blocking=True), ids_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True)
-        losses = trainer.train_step(model, opt, a, b, c, alpha)
-        return torch.stack(losses).cpu()
+    def step_resident():
+        if graphed is None:
+            return step_eager()
+        return graphed(pv, ids, mask, alpha)
 
+    def step_e2e():
+        if graphed is None:
+            a, b, c = pv_h.to(dev, non_blocking=True), ids_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True)
+            return torch.stack(trainer.train_step(model, opt, a, b, c, alpha)).cpu()
+        return graphed(pv_h, ids_h, mask_h, alpha).cpu()      # pinned host batch -> static device buffers -> replay
+
+    if graphed is not None:
+        try:
+            step_resident()
+        except Exception as ex:                               # noqa: BLE001  (e.g. a collective that cannot be captured)
+            if rank == 0:
+                print("graph capture failed (%s: %s); falling back to eager launches" % (type(ex).__name__, ex), file=sys.stderr)
+            graphed = None
+
+    _lib.reset_launch_count()
+    step_eager()                                   # one eager step counts this step's kernel launches
+    launches_per_step = _lib.launch_count()
     for _ in range(args.warmup):
         last = step_resident()
     sync()
@@ -219,17 +238,21 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         last = step_resident()
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps    # CPU time to ENQUEUE one step (no sync inside)
     e1.record()
     sync()
     launches = _lib.launch_count()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
-    losses = [float(x.detach()) for x in last]
+    losses = [float(x) for x in (last.detach() if torch.is_tensor(last) else torch.stack([l.detach() for l in last]))]
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps, "gpu_launches": launches}), flush=True)
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps, "gpu_launches": launches_per_step * args.steps,
+                              "graph": graphed is not None,
+                              "host_enqueue_ms_per_step": host_ms}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -251,7 +274,7 @@ def run_ours(args):
 
     roof, extra = None, None
     if rank == 0:
-        roof, extra = kernel_rooflines(torch, kernels, model, step_resident, B, world)
+        roof, extra = kernel_rooflines(torch, kernels, model, step_eager, B, world)
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -270,7 +293,9 @@ def run_ours(args):
             "e2e": {"value": B * world / (ms_e2e / args.steps / 1e3), "unit": "molecules/s",
                     "h2d_bytes_per_step": (pv_h.numel() * 4 + ids_h.numel() * 8 + mask_h.numel() * 8),
                     "d2h_bytes_per_step": 16},
-            "gpu_launches": launches, "clocks": clocks, "losses_last_step": losses,
+            "gpu_launches": launches if graphed is None else launches_per_step * args.steps,
+            "launch_mode": "eager" if graphed is None else "cuda_graph (one captured graph of the whole step, replayed)",
+            "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "losses_last_step": losses,
             "step_tflops": fl / (ms_step / 1e3) / 1e12,
             "step_frac_of_bf16_sustained": fl / (ms_step / 1e3) / 1e12 / (pk["bf16_tflops_sustained"] * world),
             "roofline": roof, "roofline_extra": extra, "peaks": pk}
@@ -337,6 +362,7 @@ def main():
     ap.add_argument("--seq-len", type=int, default=64)
     ap.add_argument("--ragged", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch kernels from Python instead of replaying the step's CUDA graph")
     ap.add_argument("--profile", action="store_true", help="bare loop for ncu: no e2e / instrumented / CPU legs")
     args = ap.parse_args()
     if args.impl == "reference":

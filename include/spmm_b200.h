@@ -20,6 +20,9 @@ extern "C" {
 #endif
 
 int spmm_version(void);
+/* Device u64 added (times a constant) to every dropout / sampler seed inside the kernels; NULL disables.  Lets a CUDA
+ * graph of the training step replay with fresh randomness: the step bumps the scalar, per-op seeds stay baked. */
+int spmm_set_rng_salt_ptr(const unsigned long long* dev_ptr);
 
 /* ------------------------------------------------------------------ GEMM (tcgen05 / TMEM / TMA)
  * C[M,N] (+)= epilogue(alpha * A[M,K] . B[N,K]^T).  Operand majors: 0 = K-major (row-major [rows][K],
@@ -145,7 +148,8 @@ int spmm_ema_multi(const float* p, float* p_m, void* p_bf16, void* p_m_bf16, int
 int spmm_grad_sumsq(const float* g, int64_t n, float* sumsq_out, void* stream);
 int spmm_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm,
-                    float grad_scale, const float* skip_flag, void* stream);
+                    float grad_scale, const float* skip_flag, const float* hyper_dev, void* stream);
+/* hyper_dev (device float[3] = lr, 1-beta1^t, sqrt(1-beta2^t)) overrides lr/step when non-NULL (graph replay). */
 
 #ifdef __cplusplus
 }

@@ -228,8 +228,8 @@ class SPMM(_Base):
         pos_prop = fusion(prop_embeds, None, text_embeds, tmask)[:, 0, :]
         pos_text = fusion(text_embeds, tmask, prop_embeds, None)[:, 0, :]
         if neg_idx is None:
-            self._step += 1
-            neg_t2i, neg_i2t = ops.sample_negatives(side, self.sampler_seed, self._step)                # :154-178
+            # per-step variation comes from the device RNG salt (ops.StepRng), so the draw is CUDA-graph safe
+            neg_t2i, neg_i2t = ops.sample_negatives(side, self.sampler_seed, 0)                         # :154-178
         else:
             neg_t2i = torch.as_tensor(neg_idx[0], device=pv.device, dtype=torch.int32)
             neg_i2t = torch.as_tensor(neg_idx[1], device=pv.device, dtype=torch.int32)

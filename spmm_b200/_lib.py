@@ -22,6 +22,7 @@ GEMM_OUT_F32, GEMM_ACCUMULATE, GEMM_GELU, GEMM_DGELU = 1, 2, 4, 8
 
 SIGNATURES = {
     "spmm_version": (i32, []),
+    "spmm_set_rng_salt_ptr": (i32, [vp]),
     "spmm_gemm_bf16": (i32, [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, C.POINTER(GemmEpilogue), vp]),
     "spmm_gemm_debug_config": (i32, [i32, i32, i32, i32]),
     "spmm_attn_fwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, f32, f32, u64, vp]),
@@ -51,7 +52,7 @@ SIGNATURES = {
     "spmm_mpm_loss_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "spmm_ema_multi": (i32, [vp, vp, vp, vp, i64, f32, f32, vp]),
     "spmm_grad_sumsq": (i32, [vp, i64, vp, vp]),
-    "spmm_adamw_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp, vp]),
+    "spmm_adamw_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp, vp, vp]),
 }
 
 

@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "spmm_b200.h"
 
+const unsigned long long* spmm_g_rng_salt = nullptr;
+
 namespace spmm {
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
@@ -54,8 +56,10 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ g
 __global__ void __launch_bounds__(256)
 adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m1, float4* __restrict__ m2,
              int64_t n4, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
-             const float* __restrict__ sumsq, float max_norm, float gscale, const float* __restrict__ skip) {
+             const float* __restrict__ sumsq, float max_norm, float gscale, const float* __restrict__ skip,
+             const float* __restrict__ hyper) {
   if (skip != nullptr && *skip != 0.f) return;
+  if (hyper != nullptr) { lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2]; }  // per-step values from device memory (CUDA graphs)
   float coef = gscale;
   if (sumsq != nullptr && max_norm > 0.f) {
     const float total = sqrtf(*sumsq) * gscale;
@@ -183,6 +187,11 @@ using namespace spmm;
 
 extern "C" int spmm_version(void) { return 100; }
 
+extern "C" int spmm_set_rng_salt_ptr(const unsigned long long* dev_ptr) {
+  spmm_g_rng_salt = dev_ptr;
+  return 0;
+}
+
 extern "C" int spmm_ema_multi(const float* p, float* p_m, void* p_bf16, void* p_m_bf16, int64_t n, float momentum,
                               float one_minus_momentum, void* stream) {
   SPMM_ARG(p && p_m && n >= 0 && n % 4 == 0);
@@ -215,7 +224,7 @@ extern "C" int spmm_grad_sumsq(const float* g, int64_t n, float* sumsq_out, void
 
 extern "C" int spmm_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                                float beta1, float beta2, float eps, float weight_decay, int step, const float* sumsq,
-                               float max_norm, float grad_scale, const float* skip_flag, void* stream) {
+                               float max_norm, float grad_scale, const float* skip_flag, const float* hyper_dev, void* stream) {
   SPMM_ARG(p && g && exp_avg && exp_avg_sq && n >= 0 && n % 4 == 0 && step >= 1);
   SPMM_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0);
   if (n == 0) return 0;
@@ -223,7 +232,7 @@ extern "C" int spmm_adamw_step(float* p, const float* g, float* exp_avg, float* 
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adamw_kernel<<<flat_grid(n / 4, 8), 256, 0, (cudaStream_t)stream>>>(
       (float4*)p, (const float4*)g, (float4*)exp_avg, (float4*)exp_avg_sq, n / 4, lr, beta1, beta2, eps, weight_decay,
-      (float)bc1, (float)sqrt(bc2), sumsq, max_norm, grad_scale, skip_flag);
+      (float)bc1, (float)sqrt(bc2), sumsq, max_norm, grad_scale, skip_flag, hyper_dev);
   SPMM_CHECK_LAUNCH();
   return 0;
 }

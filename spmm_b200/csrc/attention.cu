@@ -71,7 +71,9 @@ __global__ void __launch_bounds__(QT * 2)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
                 const __nv_bfloat16* __restrict__ v, int ldv, __nv_bfloat16* __restrict__ o, int ldo,
                 float* __restrict__ lse, int heads, int Tq, int Tk, const int* __restrict__ kv_len, int causal,
-                int kv_bstride, float scale, unsigned long long seed, uint32_t thresh16, float inv_keep) {
+                int kv_bstride, float scale, unsigned long long seed, uint32_t thresh16, float inv_keep,
+                const unsigned long long* salt) {
+  if (thresh16) seed = salted(seed, salt);
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* pQ = smem;
   uint8_t* pK = pQ + QT * 128;
@@ -175,7 +177,9 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ dO, int lddo, const __nv_bfloa
                 const __nv_bfloat16* __restrict__ o, int ldo, const float* __restrict__ lse,
                 __nv_bfloat16* __restrict__ dq, int lddq, __nv_bfloat16* __restrict__ dk, int lddk,
                 __nv_bfloat16* __restrict__ dv, int lddv, int heads, int Tq, int Tk, const int* __restrict__ kv_len,
-                int causal, float scale, unsigned long long seed, uint32_t thresh16, float inv_keep) {
+                int causal, float scale, unsigned long long seed, uint32_t thresh16, float inv_keep,
+                const unsigned long long* salt) {
+  if (thresh16) seed = salted(seed, salt);
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* pQ = smem;               // [QT][64]
   uint8_t* pdO = pQ + QT * 128;     // [QT][64]
@@ -337,7 +341,7 @@ extern "C" int spmm_attn_fwd(const void* q, int ldq, const void* k, int ldk, con
     if (!cfg) { cudaFuncSetAttribute(attn_fwd_kernel<QTV, KTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem); cfg = true; } \
     attn_fwd_kernel<QTV, KTV><<<grid, QTV * 2, kSmem, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, \
                                                   (const __nv_bfloat16*)v, ldv, (__nv_bfloat16*)o, ldo, lse, heads,  \
-                                                  Tq, Tk, kv_len, causal, kv_batch_stride_rows, scale, seed, th, ik); \
+                                                  Tq, Tk, kv_len, causal, kv_batch_stride_rows, scale, seed, th, ik, spmm_g_rng_salt); \
   }
   if (QT == 64 && KT == 64) SPMM_ATTN_FWD(64, 64) else if (QT == 64) SPMM_ATTN_FWD(64, 128)
   else if (KT == 64) SPMM_ATTN_FWD(128, 64) else SPMM_ATTN_FWD(128, 128)
@@ -370,7 +374,7 @@ extern "C" int spmm_attn_bwd(const void* d_o, int lddo, const void* q, int ldq, 
     attn_bwd_kernel<QTV, KTV><<<grid, QTV * 2, kSmem, st>>>(                                                          \
         (const __nv_bfloat16*)d_o, lddo, (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk,                  \
         (const __nv_bfloat16*)v, ldv, (const __nv_bfloat16*)o, ldo, lse, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, \
-        lddk, (__nv_bfloat16*)dv, lddv, heads, Tq, Tk, kv_len, causal, scale, seed, th, ik);                          \
+        lddk, (__nv_bfloat16*)dv, lddv, heads, Tq, Tk, kv_len, causal, scale, seed, th, ik, spmm_g_rng_salt);         \
   }
   if (QT == 64) SPMM_ATTN_BWD(64, 64) else if (KT == 64) SPMM_ATTN_BWD(128, 64) else SPMM_ATTN_BWD(128, 128)
 #undef SPMM_ATTN_BWD

@@ -15,9 +15,17 @@
     if (!(cond)) return -1; \
   } while (0)
 
+// Device scalar added to every dropout / sampler seed (set with spmm_set_rng_salt_ptr).  A training step bumps it
+// once, so a CUDA graph of the step replays with fresh randomness although the per-op seeds are baked in.
+extern const unsigned long long* spmm_g_rng_salt;
+
 namespace spmm {
 
 constexpr int kNumSMs = 148;
+
+__device__ __forceinline__ unsigned long long salted(unsigned long long seed, const unsigned long long* salt) {
+  return salt ? seed + __ldg(salt) * 0x9E3779B97F4A7C15ull : seed;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

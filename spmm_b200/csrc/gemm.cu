@@ -42,6 +42,7 @@ struct GemmParams {
   uint32_t drop_thresh16;  // keep iff 16-bit draw >= thresh
   float drop_inv_keep;
   uint32_t mn_lbo, mn_sbo;  // MN-major descriptor strides (bytes)
+  const unsigned long long* salt;  // device RNG salt (may be null)
   int debug_nomma;           // debug: consume stages without issuing MMAs (TMA ingest measurement)
   int splits, kb_per_split;  // split-K (fp32 accumulate outputs only): partials are reduced with red.global.add
 };
@@ -68,6 +69,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const int m0,
   const bool out_f32 = p.flags & SPMM_GEMM_OUT_F32, accum = p.flags & SPMM_GEMM_ACCUMULATE;
   const bool do_gelu = p.flags & SPMM_GEMM_GELU, do_dgelu = p.flags & SPMM_GEMM_DGELU;
   const bool do_drop = p.drop_thresh16 != 0;
+  const unsigned long long drop_seed = do_drop ? salted(p.drop_seed, p.salt) : 0ull;
   const int row = m0 + q * 32 + lane;
   const bool row_ok = row < p.M;
   const __nv_bfloat16* side = do_dgelu ? p.aux : p.residual;  // at most one bf16 side input per call
@@ -139,7 +141,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const int m0,
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const unsigned long long e = (unsigned long long)row * (unsigned long long)p.N + (col0 + j);
-        v[j] = drop_keep16(p.drop_seed, e, p.drop_thresh16) ? v[j] * p.drop_inv_keep : 0.f;
+        v[j] = drop_keep16(drop_seed, e, p.drop_thresh16) ? v[j] * p.drop_inv_keep : 0.f;
       }
     }
     if (side != nullptr) {
@@ -655,6 +657,7 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   p.alpha = 1.f;
   p.mn_lbo = g_mn_lbo; p.mn_sbo = g_mn_sbo;
   p.debug_nomma = g_nomma;
+  p.salt = spmm_g_rng_salt;
   if (epi) {
     p.bias = epi->bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(epi->residual); p.ldr = epi->ld_residual;

@@ -30,7 +30,8 @@ template <int NCH>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
-              float eps, unsigned long long seed, uint32_t thresh16, float inv_keep) {
+              float eps, unsigned long long seed, uint32_t thresh16, float inv_keep, const unsigned long long* salt) {
+  if (thresh16) seed = salted(seed, salt);
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -89,7 +90,9 @@ ln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                  __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_branch, int rows, int H,
                  unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep, unsigned long long br_seed,
-                 uint32_t br_thresh, float br_inv_keep) {
+                 uint32_t br_thresh, float br_inv_keep, const unsigned long long* salt) {
+  if (out_thresh) out_seed = salted(out_seed, salt);
+  if (br_thresh) br_seed = salted(br_seed, salt);
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -141,7 +144,9 @@ __global__ void __launch_bounds__(256)
 ln_bwd_param_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                     const float* __restrict__ mean, const float* __restrict__ rstd,
                     const __nv_bfloat16* __restrict__ branch, float* dgamma, float* dbeta, float* dbias, int rows, int H,
-                    int rows_per_block, unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep) {
+                    int rows_per_block, unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep,
+                    const unsigned long long* salt) {
+  if (out_thresh) out_seed = salted(out_seed, salt);
   __shared__ float sh[3][8][33 * 8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + lane * 8;
@@ -208,7 +213,7 @@ extern "C" int spmm_layernorm_fwd(const void* x, const float* gamma, const float
   const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   const int nch = (H + 255) / 256;
   cudaStream_t st = (cudaStream_t)stream;
-#define SPMM_LN_FWD(N) ln_fwd_kernel<N><<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, H, eps, seed, th, ik)
+#define SPMM_LN_FWD(N) ln_fwd_kernel<N><<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, H, eps, seed, th, ik, spmm_g_rng_salt)
   if (nch == 1) SPMM_LN_FWD(1); else if (nch == 2) SPMM_LN_FWD(2); else if (nch == 3) SPMM_LN_FWD(3); else SPMM_LN_FWD(4);
 #undef SPMM_LN_FWD
   SPMM_CHECK_LAUNCH();
@@ -230,7 +235,7 @@ extern "C" int spmm_layernorm_bwd(const void* dy, const void* x, const float* me
   const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   const int nch = (H + 255) / 256;
   cudaStream_t st = (cudaStream_t)stream;
-#define SPMM_LN_BWD(N) ln_bwd_dx_kernel<N><<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_branch, rows, H, out_seed, oth, oik, branch_seed, bth, bik)
+#define SPMM_LN_BWD(N) ln_bwd_dx_kernel<N><<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_branch, rows, H, out_seed, oth, oik, branch_seed, bth, bik, spmm_g_rng_salt)
   if (nch == 1) SPMM_LN_BWD(1); else if (nch == 2) SPMM_LN_BWD(2); else if (nch == 3) SPMM_LN_BWD(3); else SPMM_LN_BWD(4);
 #undef SPMM_LN_BWD
   SPMM_CHECK_LAUNCH();
@@ -243,7 +248,7 @@ extern "C" int spmm_layernorm_bwd(const void* dy, const void* x, const float* me
     const __nv_bfloat16* branch = (const __nv_bfloat16*)(dx_branch ? dx_branch : dx);
     ln_bwd_param_kernel<<<dim3(col_blocks, row_blocks), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
                                                                      mean, rstd, branch, dgamma, dbeta, dbias, rows, H, rpb,
-                                                                     out_seed, oth, oik);
+                                                                     out_seed, oth, oik, spmm_g_rng_salt);
     SPMM_CHECK_LAUNCH();
   }
   return 0;

@@ -37,7 +37,8 @@ __device__ __forceinline__ float exact_exp_neg(float x) {
 // one warp per (stream, row): stream 0 = t2i (negative property for each text), 1 = i2t (negative text per property)
 __global__ void sample_neg_kernel(const float* __restrict__ sim_i2t, const float* __restrict__ sim_t2i, int B,
                                   uint32_t seed_lo, uint32_t seed_hi, uint32_t step_lo, uint32_t step_hi,
-                                  int* __restrict__ neg_t2i, int* __restrict__ neg_i2t) {
+                                  int* __restrict__ neg_t2i, int* __restrict__ neg_i2t,
+                                  const unsigned long long* __restrict__ salt) {
   extern __shared__ float shw[];  // [warps][B]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int job = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -51,7 +52,9 @@ __global__ void sample_neg_kernel(const float* __restrict__ sim_i2t, const float
   for (int j = lane; j < B; j += 32) w[j] = (j == b) ? 0.f : exact_exp_neg(__fsub_rn(row[j], mx));  // fill_diagonal_(0)
   __syncwarp();
   if (lane == 0) {
-    uint32_t c[4] = {(uint32_t)b, (uint32_t)stream, step_lo, step_hi};
+    // the device salt (bumped once per training step) is folded into the Philox counter's step words
+    const unsigned long long step = (((unsigned long long)step_hi << 32) | step_lo) + (salt ? __ldg(salt) : 0ull);
+    uint32_t c[4] = {(uint32_t)b, (uint32_t)stream, (uint32_t)step, (uint32_t)(step >> 32)};
     philox4x32_10(seed_lo, seed_hi, c);
     const float u = __fmul_rn((float)(c[0] >> 8), 5.9604644775390625e-8f);  // [0,1), 24 bits
     float total = 0.f;
@@ -96,7 +99,7 @@ extern "C" int spmm_sample_negatives(const float* sim_i2t, const float* sim_t2i,
   const int warps = 4;
   sample_neg_kernel<<<(2 * B + warps - 1) / warps, warps * 32, (size_t)warps * B * sizeof(float), (cudaStream_t)stream>>>(
       sim_i2t, sim_t2i, B, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, (uint32_t)(step >> 32), neg_t2i,
-      neg_i2t);
+      neg_i2t, spmm_g_rng_salt);
   SPMM_CHECK_LAUNCH();
   return 0;
 }

@@ -199,10 +199,11 @@ def grad_sumsq(g, out):
     call("spmm_grad_sumsq", g.data_ptr(), g.numel(), out.data_ptr(), _st())
 
 
-def adamw(p, g, m1, m2, lr, beta1, beta2, eps, wd, step, sumsq=None, max_norm=0.0, grad_scale=1.0, skip_flag=None):
+def adamw(p, g, m1, m2, lr, beta1, beta2, eps, wd, step, sumsq=None, max_norm=0.0, grad_scale=1.0, skip_flag=None,
+          hyper_dev=None):
     call("spmm_adamw_step", p.data_ptr(), g.data_ptr(), m1.data_ptr(), m2.data_ptr(), p.numel(), float(lr), float(beta1),
          float(beta2), float(eps), float(wd), int(step), _p(sumsq), float(max_norm), float(grad_scale), _p(skip_flag),
-         _st())
+         _p(hyper_dev), _st())
 
 
 def embed_text_fwd(ids, word, pos, type0, H):
@@ -244,3 +245,8 @@ def pv_tokens_bwd(dprop, pv, mpm_mask, dw, db, dcls, dmask):
     B, n_prop = pv.shape
     call("spmm_pv_tokens_bwd", dprop.data_ptr(), pv.data_ptr(), mpm_mask.data_ptr(), dw.data_ptr(), db.data_ptr(),
          dcls.data_ptr(), dmask.data_ptr(), B, n_prop, dprop.shape[-1], _st())
+
+
+def set_rng_salt(dev_tensor):
+    """Registers the device int64 scalar the kernels add to every dropout / sampler seed (None clears it)."""
+    call("spmm_set_rng_salt_ptr", _p(dev_tensor))

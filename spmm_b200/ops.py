@@ -38,6 +38,37 @@ def next_seed():
     return ((_rng.seed * 0x9E3779B97F4A7C15) + _rng.counter * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
 
 
+class StepRng:
+    """Per-training-step randomness that survives CUDA-graph replay.
+
+    Per-op seeds (`next_seed()`) are host integers and get baked into a captured graph; the kernels therefore add a
+    DEVICE scalar ("salt") to every seed.  `advance()` bumps the salt in pinned host memory and enqueues a
+    pinned->device copy on the current stream: captured once, the copy node re-reads the host value on every replay.
+    """
+
+    def __init__(self, device):
+        if torch.device(device).type != "cuda":
+            raise K._lib.SpmmKernelError("StepRng lives on the GPU the kernels run on, got %s" % (device,))
+        self.host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.dev = torch.zeros(1, dtype=torch.int64, device=device)
+        K.set_rng_salt(self.dev)
+
+    def advance(self):
+        self.host += 1
+        self.dev.copy_(self.host, non_blocking=True)
+
+
+_step_rngs = {}
+
+
+def step_rng(device):
+    device = torch.device(device)
+    r = _step_rngs.get(device)
+    if r is None:
+        r = _step_rngs[device] = StepRng(device)
+    return r
+
+
 def _wgrad(dy, x, gw, n_out, k_in, m_tokens):
     """gw[n_out, k_in] += dy^T . x  (both operands MN-major: no transpose pass)."""
     if gw is not None:

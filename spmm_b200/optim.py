@@ -21,20 +21,36 @@ class FusedClipAdamW(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros(n, device=self.A.device, dtype=torch.float32)
         self.max_norm = max_norm
         self.t = 0
+        # per-step scalars (lr, 1-beta1^t, sqrt(1-beta2^t)) travel through pinned host memory -> device so that a
+        # captured CUDA graph of the step picks up fresh values on every replay
+        self.hyper_host = torch.zeros(3, dtype=torch.float32).pin_memory()
+        self.hyper_dev = torch.zeros(3, dtype=torch.float32, device=self.A.device)
 
     def zero_grad(self, set_to_none=False):
         self.A.ensure_grads()
         self.A.zero_grad()
 
-    @torch.no_grad()
-    def step(self, closure=None, skip_flag=None, grad_scale=1.0):
-        A, g0 = self.A, self.A.adam_start
+    def prepare_step(self):
+        """Host side of a step: advance t and publish (lr, bias corrections) to pinned memory.  Called once per step
+        BEFORE the (possibly graph-replayed) device work."""
         grp = self.param_groups[0]
         self.t += 1
+        b1, b2 = grp["betas"]
+        self.hyper_host[0] = grp["lr"]
+        self.hyper_host[1] = 1.0 - b1 ** self.t
+        self.hyper_host[2] = (1.0 - b2 ** self.t) ** 0.5
+
+    @torch.no_grad()
+    def step(self, closure=None, skip_flag=None, grad_scale=1.0, prepared=False):
+        A, g0 = self.A, self.A.adam_start
+        grp = self.param_groups[0]
+        if not prepared:
+            self.prepare_step()
+        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
         K.grad_sumsq(A.G[g0:], A.sumsq)
         K.adamw(A.P[g0:], A.G[g0:], self.exp_avg, self.exp_avg_sq, grp["lr"], grp["betas"][0], grp["betas"][1], grp["eps"],
-                grp["weight_decay"], self.t, sumsq=A.sumsq, max_norm=self.max_norm, grad_scale=grad_scale,
-                skip_flag=skip_flag)
+                grp["weight_decay"], max(self.t, 1), sumsq=A.sumsq, max_norm=self.max_norm, grad_scale=grad_scale,
+                skip_flag=skip_flag, hyper_dev=self.hyper_dev)
 
     def grad_norm(self, grad_scale=1.0):
         """Total gradient L2 norm of the last step() (device scalar)."""

@@ -197,3 +197,32 @@ def test_three_training_steps_track_the_oracle_trajectory():
     for a, b in zip(ours, ref):
         assert all(abs(x - y) <= 3e-2 for x, y in zip(a, b)), (a, b)
     assert int(model.queue_ptr) == ptr
+
+
+def test_cuda_graph_step_matches_eager_step():
+    """GraphedTrainStep (one captured CUDA graph of the whole step) must reproduce the eager launches: eval mode,
+    injected PV mask; negatives come from the device sampler whose stream is driven by the step salt in both modes."""
+    from spmm_b200 import ops, trainer
+    from spmm_b200.optim import FusedClipAdamW
+    g = load_golden("tiny_b6")
+    pv, ids, mask, mpm = g["pv"].to(DEV), g["ids"].to(DEV), g["mask"].to(DEV), g["mpm_mask"].to(DEV)
+    out = {}
+    for mode in ("eager", "graph"):
+        model = build_model("tiny_b6")
+        opt = FusedClipAdamW(model, lr=2e-4, weight_decay=0.02)
+        ops.step_rng(DEV).host.zero_()
+        stepper = trainer.GraphedTrainStep(model, opt) if mode == "graph" else None
+        hist = []
+        for it in range(4):
+            if stepper is None:
+                l = torch.stack([x.detach() for x in trainer.train_step(model, opt, pv, ids, mask, 0.4, mpm_mask=mpm)])
+            else:
+                l = stepper(pv, ids, mask, 0.4, mpm_mask=mpm).clone()
+            hist.append(l.cpu())
+        out[mode] = (torch.stack(hist), model.text_encoder.bert.encoder.layer[1].output.dense.weight.detach().clone(),
+                     int(model.queue_ptr), model.last_aux["neg_t2i"].tolist())
+    print("eager", out["eager"][0].tolist())
+    print("graph", out["graph"][0].tolist())
+    assert torch.allclose(out["eager"][0], out["graph"][0], atol=2e-3), (out["eager"][0], out["graph"][0])
+    assert torch.allclose(out["eager"][1], out["graph"][1], atol=1e-5)
+    assert out["eager"][2] == out["graph"][2] and out["eager"][3] == out["graph"][3]
