@@ -225,8 +225,6 @@ class SPMM(_Base):
         def fusion(q, q_mask, kv, kv_mask, dec=False):
             return te.bert(encoder_embeds=q, attention_mask=q_mask, encoder_hidden_states=kv,
                            encoder_attention_mask=kv_mask, is_decoder=dec, mode='fusion').last_hidden_state
-        pos_prop = fusion(prop_embeds, None, text_embeds, tmask)[:, 0, :]
-        pos_text = fusion(text_embeds, tmask, prop_embeds, None)[:, 0, :]
         if neg_idx is None:
             # per-step variation comes from the device RNG salt (ops.StepRng), so the draw is CUDA-graph safe
             neg_t2i, neg_i2t = ops.sample_negatives(side, self.sampler_seed, 0)                         # :154-178
@@ -235,12 +233,14 @@ class SPMM(_Base):
             neg_i2t = torch.as_tensor(neg_idx[1], device=pv.device, dtype=torch.int32)
         prop_neg = ops.gather_rows(prop_embeds, neg_t2i)
         text_neg = ops.gather_rows(text_embeds, neg_i2t)
-        tmask_all = MaskInfo(kv_len=torch.cat([tmask.kv_len, tmask.kv_len[neg_i2t.long()]]))
-        text_all = torch.cat([text_embeds, text_neg], dim=0)
-        prop_all = torch.cat([prop_neg, prop_embeds], dim=0)
-        neg_prop = fusion(prop_all, None, text_all, tmask_all)[:, 0, :]
-        neg_text = fusion(text_all, tmask_all, prop_all, None)[:, 0, :]
-        vl = torch.cat([torch.cat([pos_prop, pos_text], dim=-1), torch.cat([neg_prop, neg_text], dim=-1)], dim=0)
+        # The reference runs the positive pairs (B) and the negative pairs (2B) as four fusion passes (:137-198).  The
+        # rows are independent, so they are batched into two passes of 3B pairs: [pos | neg-prop | neg-text].
+        tmask3 = MaskInfo(kv_len=torch.cat([tmask.kv_len, tmask.kv_len, tmask.kv_len[neg_i2t.long()]]))
+        text3 = torch.cat([text_embeds, text_embeds, text_neg], dim=0)
+        prop3 = torch.cat([prop_embeds, prop_neg, prop_embeds], dim=0)
+        out_prop = fusion(prop3, None, text3, tmask3)[:, 0, :]
+        out_text = fusion(text3, tmask3, prop3, None)[:, 0, :]
+        vl = torch.cat([out_prop, out_text], dim=-1)              # rows [0,B) positives, [B,3B) negatives (:199-201)
         loss_itm = ops.itm_loss(vl, W["itm"], B)
 
         self._dequeue_and_enqueue(side["feat_prop_m"], side["feat_text_m"], nan_flag)                   # :208

@@ -208,10 +208,24 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return h;
 }
+// 64-bit (seed + step salt) -> 32-bit key, once per kernel
+__device__ __forceinline__ uint32_t fold_seed(unsigned long long s) {
+  return mix32((uint32_t)s ^ mix32((uint32_t)(s >> 32) + 0x9E3779B9u));
+}
+// 2 x 16 random bits for elements (e_even, e_even + 1): ONE mix per pair of elements
+__device__ __forceinline__ uint32_t drop_bits2(uint32_t key, uint32_t e_even) {
+  return mix32((e_even >> 1) * 0x9E3779B1u + key);
+}
 __device__ __forceinline__ bool keep16(unsigned long long seed, unsigned long long e, uint32_t thresh16) {
-  const uint32_t pair = (uint32_t)(e >> 1);
-  const uint32_t h = mix32(pair * 0x9E3779B1u + (uint32_t)seed + mix32((uint32_t)(e >> 33) ^ (uint32_t)(seed >> 32)));
+  const uint32_t h = drop_bits2(fold_seed(seed), (uint32_t)e & ~1u);
   return ((h >> (16 * (e & 1))) & 0xFFFFu) >= thresh16;
+}
+// apply the mask to an (even, odd) element pair
+__device__ __forceinline__ void drop_pair(uint32_t key, uint32_t e_even, uint32_t thresh16, float inv_keep, float& a,
+                                          float& b) {
+  const uint32_t h = drop_bits2(key, e_even);
+  a = ((h & 0xFFFFu) >= thresh16) ? a * inv_keep : 0.f;
+  b = ((h >> 16) >= thresh16) ? b * inv_keep : 0.f;
 }
 // keep-probability test: returns scale (1/(1-p)) or 0
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, uint32_t thresh, float inv_keep) {

@@ -69,7 +69,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const int m0,
   const bool out_f32 = p.flags & SPMM_GEMM_OUT_F32, accum = p.flags & SPMM_GEMM_ACCUMULATE;
   const bool do_gelu = p.flags & SPMM_GEMM_GELU, do_dgelu = p.flags & SPMM_GEMM_DGELU;
   const bool do_drop = p.drop_thresh16 != 0;
-  const unsigned long long drop_seed = do_drop ? salted(p.drop_seed, p.salt) : 0ull;
+  const uint32_t drop_key = do_drop ? fold_seed(salted(p.drop_seed, p.salt)) : 0u;
   const int row = m0 + q * 32 + lane;
   const bool row_ok = row < p.M;
   const __nv_bfloat16* side = do_dgelu ? p.aux : p.residual;  // at most one bf16 side input per call
@@ -139,9 +139,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const int m0,
     }
     if (do_drop) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const unsigned long long e = (unsigned long long)row * (unsigned long long)p.N + (col0 + j);
-        v[j] = drop_keep16(drop_seed, e, p.drop_thresh16) ? v[j] * p.drop_inv_keep : 0.f;
+      for (int j = 0; j < 32; j += 2) {   // element index row*N + col is even here (N % 8 == 0, col0 % 32 == 0)
+        const uint32_t e = (uint32_t)row * (uint32_t)p.N + (uint32_t)(col0 + j);
+        drop_pair(drop_key, e, p.drop_thresh16, p.drop_inv_keep, v[j], v[j + 1]);
       }
     }
     if (side != nullptr) {
@@ -269,6 +269,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int m0 = (mn % num_m) * BM, n0 = (mn / num_m) * BN;
       const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
+        if (p.debug_nomma == 2) continue;   // debug: MMA-only timing, nothing is loaded
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + A_STAGE_BYTES;
@@ -302,9 +303,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int sp = tile / num_mn;
       const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        if (p.debug_nomma != 2) mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (p.debug_nomma) {
+        if (p.debug_nomma == 1) {
           mbar_arrive(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           continue;
@@ -322,7 +323,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      if (p.debug_nomma) mbar_arrive(&tfull_bar[acc]);
+      if (p.debug_nomma == 1) mbar_arrive(&tfull_bar[acc]);
       else tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -639,7 +640,7 @@ extern "C" int spmm_gemm_debug_config(int mn_lbo_bytes, int mn_sbo_bytes, int fo
   g_force_bn = force_bn & 0xFFFF;
   g_split_k = (force_bn & 0x10000) ? 0 : 1;   // bit 16 disables split-K (debug / A-B measurements)
   g_use_2cta = (force_bn & 0x40000) ? 0 : 1;  // bit 18 disables the 2-CTA kernel
-  g_nomma = (force_bn & 0x20000) ? 1 : 0;     // bit 17: skip MMAs (TMA-only pipeline timing; results are garbage)
+  g_nomma = (force_bn & 0x20000) ? 1 : ((force_bn & 0x80000) ? 2 : 0);   // bit 19: MMA-only (no TMA, garbage results)     // bit 17: skip MMAs (TMA-only pipeline timing; results are garbage)
   g_max_ctas = max_ctas;
   return 0;
 }

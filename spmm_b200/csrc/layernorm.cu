@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
               float eps, unsigned long long seed, uint32_t thresh16, float inv_keep, const unsigned long long* salt) {
-  if (thresh16) seed = salted(seed, salt);
+  const uint32_t key = thresh16 ? fold_seed(salted(seed, salt)) : 0u;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -74,9 +74,10 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
       load8f(gamma + col, g);
       load8f(beta + col, b);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        o[j] = (v[c][j] - mean) * rstd * g[j] + b[j];
-        if (thresh16) o[j] = keep16(seed, (unsigned long long)row * H + col + j, thresh16) ? o[j] * inv_keep : 0.f;
+      for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * g[j] + b[j];
+      if (thresh16) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) drop_pair(key, (uint32_t)row * H + col + j, thresh16, inv_keep, o[j], o[j + 1]);
       }
       store8(yr + col, o);
     }
@@ -91,8 +92,8 @@ ln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
                  __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_branch, int rows, int H,
                  unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep, unsigned long long br_seed,
                  uint32_t br_thresh, float br_inv_keep, const unsigned long long* salt) {
-  if (out_thresh) out_seed = salted(out_seed, salt);
-  if (br_thresh) br_seed = salted(br_seed, salt);
+  const uint32_t out_key = out_thresh ? fold_seed(salted(out_seed, salt)) : 0u;
+  const uint32_t br_key = br_thresh ? fold_seed(salted(br_seed, salt)) : 0u;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -108,9 +109,12 @@ ln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
       load8(dy + (size_t)row * H + col, d);
       load8f(gamma + col, gm);
 #pragma unroll
+      if (out_thresh) {  // forward applied dropout after the affine: dy_affine = dy * mask / keep
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) drop_pair(out_key, (uint32_t)row * H + col + j, out_thresh, out_inv_keep, d[j], d[j + 1]);
+      }
+#pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (out_thresh)  // forward applied dropout after the affine: dy_affine = dy * mask / keep
-          d[j] = keep16(out_seed, (unsigned long long)row * H + col + j, out_thresh) ? d[j] * out_inv_keep : 0.f;
         xh[c][j] = (xh[c][j] - mu) * rs;
         g[c][j] = d[j] * gm[j];
         s1 += g[c][j];
@@ -130,8 +134,7 @@ ln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
       store8(dx + (size_t)row * H + col, o);
       if (dx_branch) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = keep16(br_seed, (unsigned long long)row * H + col + j, br_thresh) ? o[j] * br_inv_keep : 0.f;
+        for (int j = 0; j < 8; j += 2) drop_pair(br_key, (uint32_t)row * H + col + j, br_thresh, br_inv_keep, o[j], o[j + 1]);
         store8(dx_branch + (size_t)row * H + col, o);
       }
     }
@@ -146,7 +149,7 @@ ln_bwd_param_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     const __nv_bfloat16* __restrict__ branch, float* dgamma, float* dbeta, float* dbias, int rows, int H,
                     int rows_per_block, unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep,
                     const unsigned long long* salt) {
-  if (out_thresh) out_seed = salted(out_seed, salt);
+  const uint32_t out_key = out_thresh ? fold_seed(salted(out_seed, salt)) : 0u;
   __shared__ float sh[3][8][33 * 8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + lane * 8;
@@ -161,9 +164,12 @@ ln_bwd_param_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
       load8(x + (size_t)r * H + c0, xv);
       const float mu = mean[r], rs = rstd[r];
 #pragma unroll
+      if (out_thresh) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) drop_pair(out_key, (uint32_t)r * H + c0 + j, out_thresh, out_inv_keep, d[j], d[j + 1]);
+      }
+#pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (out_thresh)
-          d[j] = keep16(out_seed, (unsigned long long)r * H + c0 + j, out_thresh) ? d[j] * out_inv_keep : 0.f;
         ag[j] += d[j] * (xv[j] - mu) * rs;
         ab[j] += d[j];
       }
