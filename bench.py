@@ -178,7 +178,14 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a stuck collective aborts after 3 minutes instead of hanging the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+
+    def log(msg):
+        if rank == 0:
+            print("[bench %.1fs] %s" % (time.perf_counter() - t_start, msg), file=sys.stderr, flush=True)
+    t_start = time.perf_counter()
     B = args.batch
     cfg = synth.pretrain_config(os.path.join(CFG, "config_bert.json"), os.path.join(CFG, "config_bert_property.json"),
                                 queue_size=36864, batch_size=B)
@@ -217,6 +224,7 @@ def run_ours(args):
             return torch.stack(trainer.train_step(model, opt, a, b, c, alpha)).cpu()
         return graphed(pv_h, ids_h, mask_h, alpha).cpu()      # pinned host batch -> static device buffers -> replay
 
+    log("model built; capturing / first step")
     if graphed is not None:
         try:
             step_resident()
@@ -225,6 +233,7 @@ def run_ours(args):
                 print("graph capture failed (%s: %s); falling back to eager launches" % (type(ex).__name__, ex), file=sys.stderr)
             graphed = None
 
+    log("first step done (graph=%s); eager counting step" % (graphed is not None))
     _lib.reset_launch_count()
     step_eager()                                   # one eager step counts this step's kernel launches
     launches_per_step = _lib.launch_count()
@@ -258,6 +267,7 @@ def run_ours(args):
         return
 
     # end-to-end through the public API with host batches
+    log("resident loop done (%.2f ms/step); e2e loop" % (ms_total / args.steps))
     step_e2e()
     sync()
     e0.record()
@@ -272,9 +282,9 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = float(t[0]), float(t[1])
 
-    roof, extra = None, None
-    if rank == 0:
-        roof, extra = kernel_rooflines(torch, kernels, model, step_eager, B, world)
+    # every rank runs the instrumented step (it contains the step's collectives); rank 0 reports it
+    log("timed regions done; instrumented step")
+    roof, extra = kernel_rooflines(torch, kernels, model, step_eager, B, world)
     if world > 1:
         dist.barrier()
     if rank != 0:

@@ -50,6 +50,8 @@ typedef struct spmm_gemm_epilogue {
 int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C,
                    int ldc, int M, int N, int K, const spmm_gemm_epilogue* epi, void* stream);
 int spmm_gemm_debug_config(int mn_lbo_bytes, int mn_sbo_bytes, int force_bn, int max_ctas);
+/* debug: device buffer of 16 x u64 per CTA receiving %globaltimer phase stamps of the next GEMM launches; NULL = off */
+int spmm_gemm_debug_trace(void* buf);
 
 /* ------------------------------------------------------------------ attention core (xbert.py:305-354)
  * softmax(Q K^T * scale + mask) V per (batch, head), head_dim 64, Tq,Tk <= 128.  q/k/v/o rows are

@@ -45,7 +45,16 @@ struct GemmParams {
   const unsigned long long* salt;  // device RNG salt (may be null)
   int debug_nomma;           // debug: consume stages without issuing MMAs (TMA ingest measurement)
   int splits, kb_per_split;  // split-K (fp32 accumulate outputs only): partials are reduced with red.global.add
+  unsigned long long* trace; // debug: per-CTA phase timestamps (16 x u64 per CTA), null in production
 };
+
+__device__ __forceinline__ void trace_mark(const GemmParams& p, int slot) {
+  if (p.trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[(size_t)blockIdx.x * 16 + slot] = t;
+  }
+}
 
 template <int BN>
 struct GemmCfg {
@@ -93,6 +102,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const int m0,
   load_side(0, side_next);
   mbar_wait(tfull, acc_phase);
   tc_fence_after();
+  if (q == 0 && lane == 0 && acc == 0 && acc_phase == 0) trace_mark(p, 5);
   const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
   for (int c = 0; c < BN / 32; ++c) {
@@ -356,13 +366,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // ------------------------------------------------------------------------------------------------ 2-CTA kernel
 // CTA pair (cluster of 2, same TPC) computes a 256 x 256 tile with tcgen05.mma.cta_group::2: each CTA stages its
 // own 128 rows of A and its own 128 columns of B (32 KB per 64-deep k-block instead of 48 KB), the leader CTA issues
-// UMMA M=256 that reads both CTAs' shared memory, and each CTA's TMEM receives its 128 output rows.  The mainloop of
-// the 1-CTA kernel is bound by L2->SM ingest (~48 B/cycle/SM measured); this halves the B traffic per FLOP.
+// UMMA M=256 that reads both CTAs' shared memory, and each CTA's TMEM receives its 128 output rows.
+//
+// Epilogue (8 warps per CTA, two per TMEM lane quadrant): accumulators go TMEM -> registers -> fused math ->
+// SWIZZLE_128B staging tile in shared memory -> ONE bulk tensor store (or f32 reduce-add) per 128x64 box, and the
+// residual / dGELU side operand arrives in the same staging tile by TMA while the mainloop runs.  A thread owns one
+// output row, so direct global stores were 16-byte pieces on 32 different lines per instruction: the phase trace
+// (tools/gemm_trace.py) showed 4-11 us of epilogue per tile against 5 us of mainloop at K=768.
 constexpr int BN2 = 256;
 constexpr int B2_STAGE_BYTES = (BN2 / 2) * BK * 2;               // this CTA's half of the B tile
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;     // 32 KB
-constexpr int kStages2 = 6;
-constexpr int SMEM2_BYTES = kStages2 * STAGE2_BYTES + 1024 + 256 + BN2 * 4;
+constexpr int kStages2 = 5;
+constexpr int STG_BOX_BYTES = 128 * 128;                         // [128 rows][128 B], 16-byte units XOR (row & 7)
+constexpr int STG_BYTES = 4 * STG_BOX_BYTES;                     // 64 KB: 128 x 256 bf16, or 128 x 128 f32
+constexpr int kThreads2 = 384;
+constexpr int SMEM2_BYTES = kStages2 * STAGE2_BYTES + STG_BYTES + 1024 /*align*/ + 512 /*barriers*/ + BN2 * 4 /*bias*/;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -380,6 +398,20 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* desc
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                 uint32_t accumulate) {
   asm volatile(
@@ -396,27 +428,92 @@ __device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {  // arrives on `b
 __device__ __forceinline__ void mbar_arrive_rank(uint64_t* bar, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // remote arrive on the leader CTA's copy
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  mbar_arrive_rank(bar, 0);
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                  const GemmParams p) {
+struct Gemm2Maps {
+  CUtensorMap a, b, c, side, pre;   // side: residual or dGELU pre-activation (bf16, same shape as C); pre: 2nd output
+};
+
+// One 32-column chunk of this thread's row: fused math on v[32], side operand / result through the staging tile.
+// Staging address of 16-byte unit u of row r in a box: box + r*128 + ((u ^ (r & 7)) << 4).
+__device__ __forceinline__ void epi2_chunk(const GemmParams& p, float (&v)[32], const float* s_bias_chunk, const int row_g,
+                                           const int col0, const uint32_t drop_key, uint8_t* out_row, uint8_t* pre_row,
+                                           const int u0, const int sw, const bool has_side) {
+  const bool out_f32 = p.flags & SPMM_GEMM_OUT_F32;
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = *reinterpret_cast<const float4*>(s_bias_chunk + 4 * i);   // smem broadcast
+      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+  }
+  if (pre_row != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 o;
+      o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+      o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      *reinterpret_cast<uint4*>(pre_row + (((u0 + i) ^ sw) << 4)) = o;
+    }
+  }
+  if (p.flags & SPMM_GEMM_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (p.drop_thresh16 != 0) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {   // element index row*N + col is even here (N % 8 == 0, col0 % 32 == 0)
+      const uint32_t e = (uint32_t)row_g * (uint32_t)p.N + (uint32_t)(col0 + j);
+      drop_pair(drop_key, e, p.drop_thresh16, p.drop_inv_keep, v[j], v[j + 1]);
+    }
+  }
+  if (has_side) {   // bf16 side operand sits where the result goes
+    const bool do_dgelu = p.flags & SPMM_GEMM_DGELU;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 sv = *reinterpret_cast<const uint4*>(out_row + (((u0 + i) ^ sw) << 4));
+      float s[8];
+      unpack_bf16x2(sv.x, s[0], s[1]); unpack_bf16x2(sv.y, s[2], s[3]);
+      unpack_bf16x2(sv.z, s[4], s[5]); unpack_bf16x2(sv.w, s[6], s[7]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * i + j] = do_dgelu ? v[8 * i + j] * dgelu_erf(s[j]) : v[8 * i + j] + s[j];
+    }
+  }
+  if (out_f32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float4*>(out_row + ((i ^ sw) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 o;
+      o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+      o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      *reinterpret_cast<uint4*>(out_row + (((u0 + i) ^ sw) << 4)) = o;
+    }
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages2 * STAGE2_BYTES);
+  uint8_t* staging = smem + kStages2 * STAGE2_BYTES;                       // 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STG_BYTES);
   uint64_t* empty_bar = full_bar + kStages2;
   uint64_t* tfull_bar = empty_bar + kStages2;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_bias = reinterpret_cast<float*>(smem + kStages2 * STAGE2_BYTES + 256);
+  uint64_t* side_full = tempty_bar + 2;     // side operand of the current tile landed in the staging tile
+  uint64_t* stage_free = side_full + 1;     // both halves' stores of the previous tile have read the staging tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
+  float* s_bias = reinterpret_cast<float*>(staging + STG_BYTES + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) trace_mark(p, 0);
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -424,10 +521,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int num_mn = num_m * num_n;
   const int num_tiles = num_mn * p.splits;
   const int num_kb_total = (p.K + BK - 1) / BK;
+  const bool out_f32 = p.flags & SPMM_GEMM_OUT_F32;
+  const bool has_side = (p.residual != nullptr) || (p.aux != nullptr);
+  const bool has_pre = p.pre != nullptr;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&maps.a);
+    tma_prefetch_desc(&maps.b);
+    tma_prefetch_desc(&maps.c);
+    if (has_side) tma_prefetch_desc(&maps.side);
+    if (has_pre) tma_prefetch_desc(&maps.pre);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages2; ++s) {
@@ -435,9 +538,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_init(&empty_bar[s], 1);   // multicast commit from the leader's MMA thread
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tfull_bar[s], 1);   // multicast commit
-      mbar_init(&tempty_bar[s], 8);  // leader's copy: 4 epilogue warps x 2 CTAs
+      mbar_init(&tfull_bar[s], 1);    // multicast commit
+      mbar_init(&tempty_bar[s], 16);  // leader's copy: 8 epilogue warps x 2 CTAs
     }
+    mbar_init(side_full, 1);
+    mbar_init(stage_free, 2);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -449,6 +554,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   cluster_sync_all();   // peer barriers initialised / TMEM allocated before any cross-CTA traffic
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_mark(p, 1);
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -465,20 +571,22 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         uint8_t* sb = sa + A_STAGE_BYTES;
         if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
         if (p.a_mn == 0) {
-          tma_load_2d_2sm(sa, &map_a, &full_bar[stage], kb * BK, m0);
+          tma_load_2d_2sm(sa, &maps.a, &full_bar[stage], kb * BK, m0);
         } else {
 #pragma unroll
-          for (int c = 0; c < BM / 64; ++c) tma_load_2d_2sm(sa + c * 8192, &map_a, &full_bar[stage], m0 + c * 64, kb * BK);
+          for (int c = 0; c < BM / 64; ++c) tma_load_2d_2sm(sa + c * 8192, &maps.a, &full_bar[stage], m0 + c * 64, kb * BK);
         }
         if (p.b_mn == 0) {
-          tma_load_2d_2sm(sb, &map_b, &full_bar[stage], kb * BK, nb0);
+          tma_load_2d_2sm(sb, &maps.b, &full_bar[stage], kb * BK, nb0);
         } else {
 #pragma unroll
-          for (int c = 0; c < BN2 / 128; ++c) tma_load_2d_2sm(sb + c * 8192, &map_b, &full_bar[stage], nb0 + c * 64, kb * BK);
+          for (int c = 0; c < BN2 / 128; ++c) tma_load_2d_2sm(sb + c * 8192, &maps.b, &full_bar[stage], nb0 + c * 64, kb * BK);
         }
         if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        if (tile == pair && kb == kb0) trace_mark(p, 2);
       }
     }
+    trace_mark(p, 9);
   } else if (warp == 1 && lane == 0 && leader) {
     // ===================== MMA issuer (leader CTA only) =====================
     const uint32_t idesc = umma_idesc_bf16(2 * BM, BN2, p.a_mn, p.b_mn);
@@ -495,6 +603,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (tile == pair && kb == kb0) trace_mark(p, 3);
         if (p.debug_nomma) {
           mbar_arrive_rank(&empty_bar[stage], 0);
           mbar_arrive_rank(&empty_bar[stage], 1);
@@ -516,28 +625,137 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       if (p.debug_nomma) { mbar_arrive_rank(&tfull_bar[acc], 0); mbar_arrive_rank(&tfull_bar[acc], 1); }
       else tc_commit_2sm(&tfull_bar[acc]);  // both CTAs' epilogues
+      if (tile == pair) trace_mark(p, 4);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue (both CTAs: own 128 rows x 256 columns) =====================
-    const int q = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+  } else if (warp == 3 && lane == 0 && has_side) {
+    // ===================== side-operand loader (both CTAs: own 128 rows) =====================
+    uint32_t ph = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int mn = tile % num_mn;
       const int m0 = (mn % num_m) * 2 * BM + (int)rank * BM, n0 = (mn / num_m) * BN2;
-      epilogue_tile<BN2>(p, m0, n0, tmem_base, acc, q, lane, s_bias, &tfull_bar[acc], acc_phase);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+      mbar_wait(stage_free, ph ^ 1);   // previous tile's stores have drained the staging tile
+      int nbox = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) nbox += (n0 + 64 * b < p.N) ? 1 : 0;
+      mbar_expect_tx(side_full, nbox * STG_BOX_BYTES);
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (n0 + 64 * b < p.N) tma_load_2d(staging + b * STG_BOX_BYTES, &maps.side, side_full, n0 + 64 * b, m0);
+      ph ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs: own 128 rows x 256 columns) =====================
+    const int q = warp & 3;             // TMEM lane quadrant this warp may read
+    const int h = (warp - 4) >> 2;      // column half: columns [128h, 128h + 128) of the tile
+    const int bar_id = 1 + h;
+    const bool elected = (warp == 4 + 4 * h) && lane == 0;
+    const int r = q * 32 + lane;        // row within this CTA's 128-row tile
+    const int sw = r & 7;
+    const uint32_t drop_key = p.drop_thresh16 ? fold_seed(salted(p.drop_seed, p.salt)) : 0u;
+    // 64-column sub-phases when a chunk needs two boxes' worth of staging (f32 output, or a 2nd bf16 output)
+    const int nsub = (out_f32 || has_pre) ? 2 : 1;
+    int acc = 0;
+    uint32_t acc_phase = 0, side_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int mn = tile % num_mn;
+      const int m0 = (mn % num_m) * 2 * BM + (int)rank * BM, n0 = (mn / num_m) * BN2;
+      const int nh0 = n0 + 128 * h;     // first column of this half
+      // staging boxes of this half are free (previous stores have read them) and the previous bias reads are done
+      if (elected) bulk_wait_read0();
+      bar_sync_named(bar_id, 128);
+      if (p.bias != nullptr) {
+        const int t = threadIdx.x - 128 - 128 * h;
+        s_bias[128 * h + t] = (nh0 + t < p.N) ? __ldg(p.bias + nh0 + t) : 0.f;
+        bar_sync_named(bar_id, 128);
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      if (has_side) mbar_wait(side_full, side_phase);
+      tc_fence_after();
+      if (warp == 4 && lane == 0 && tile == pair) trace_mark(p, 5);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN2 + 128 * h;
+      for (int sub = 0; sub < nsub; ++sub) {
+        if (sub > 0) {
+          if (elected) bulk_wait_read0();
+          bar_sync_named(bar_id, 128);
+        }
+        const int nchunk = 4 / nsub;
+        // TMEM reads are software-pipelined: the load of chunk cc+1 is in flight while chunk cc is processed
+        uint32_t rr[32];
+        if (nh0 + 32 * sub * nchunk < p.N) tmem_ld32(taddr + sub * nchunk * 32, rr);
+#pragma unroll 1
+        for (int cc = 0; cc < nchunk; ++cc) {
+          const int c = sub * nchunk + cc;            // chunk within the half: columns nh0 + 32c
+          const int col0 = nh0 + 32 * c;
+          if (col0 >= p.N) break;                     // warp-uniform
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
+          if (cc + 1 < nchunk && col0 + 32 < p.N) tmem_ld32(taddr + (c + 1) * 32, rr);
+          // staging placement: bf16 -> box 2h + (c >> 1), units 4*(c & 1)..+3; pre mode -> act box 2h+1 / pre box 2h,
+          // units 4*cc..+3; f32 -> box 2h + cc, units 0..7
+          uint8_t* out_row;
+          uint8_t* pre_row = nullptr;
+          int u0;
+          if (out_f32) { out_row = staging + (2 * h + cc) * STG_BOX_BYTES + r * 128; u0 = 0; }
+          else if (has_pre) {
+            out_row = staging + (2 * h + 1) * STG_BOX_BYTES + r * 128;
+            pre_row = staging + (2 * h) * STG_BOX_BYTES + r * 128;
+            u0 = 4 * cc;
+          } else { out_row = staging + (2 * h + (c >> 1)) * STG_BOX_BYTES + r * 128; u0 = 4 * (c & 1); }
+          epi2_chunk(p, v, s_bias + 128 * h + 32 * c, m0 + r, col0, drop_key, out_row, pre_row, u0, sw, has_side);
+        }
+        if (sub == nsub - 1) {            // accumulator fully read: hand the TMEM buffer back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+        }
+        if (warp == 4 && lane == 0 && tile == pair && sub == 0) trace_mark(p, 12);
+        fence_proxy_async();
+        bar_sync_named(bar_id, 128);
+        if (warp == 4 && lane == 0 && tile == pair && sub == 0) trace_mark(p, 13);
+        if (elected) {
+          const int cs = nh0 + sub * 64;   // first column of this sub-phase (nsub == 2)
+          if (out_f32) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+              if (cs + 32 * b < p.N) {
+                if ((p.flags & SPMM_GEMM_ACCUMULATE) || p.splits > 1)
+                  tma_reduce_add_2d(&maps.c, staging + (2 * h + b) * STG_BOX_BYTES, cs + 32 * b, m0);
+                else
+                  tma_store_2d(&maps.c, staging + (2 * h + b) * STG_BOX_BYTES, cs + 32 * b, m0);
+              }
+          } else if (has_pre) {
+            if (cs < p.N) {
+              tma_store_2d(&maps.pre, staging + (2 * h) * STG_BOX_BYTES, cs, m0);
+              tma_store_2d(&maps.c, staging + (2 * h + 1) * STG_BOX_BYTES, cs, m0);
+            }
+          } else {
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+              if (nh0 + 64 * b < p.N) tma_store_2d(&maps.c, staging + (2 * h + b) * STG_BOX_BYTES, nh0 + 64 * b, m0);
+          }
+          bulk_commit();
+        }
+      }
+      if (has_side && elected) {   // let the side loader refill the staging tile for the next tile
+        bulk_wait_read0();
+        mbar_arrive(stage_free);
+      }
+      if (warp == 4 && lane == 0) trace_mark(p, tile == pair ? 6 : 10);
+      side_phase ^= 1;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (elected) bulk_wait_read0();  // the staging tile must outlive the bulk stores' reads (writes drain with the grid)
   }
+  if (threadIdx.x == 0) trace_mark(p, 7);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // the leader's MMAs read this CTA's smem and signal its barriers: leave together
+  if (threadIdx.x == 0) trace_mark(p, 8);
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -564,14 +782,14 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows with leading dimension `ld` elements.
 static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                    uint32_t box_outer) {
+                    uint32_t box_outer, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return -2;
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * (f32 ? 4 : 2)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -3;
@@ -582,6 +800,7 @@ static int g_force_bn = 0;
 static int g_max_ctas = 0;
 static int g_split_k = 1;
 static int g_nomma = 0;
+static unsigned long long* g_trace = nullptr;
 
 template <int BN>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
@@ -603,7 +822,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
 
 static int g_use_2cta = 1;
 
-static int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+static int launch2(const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
@@ -613,7 +832,7 @@ static int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParam
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN2 - 1) / BN2) * p.splits;
   int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
   if (g_max_ctas > 0 && 2 * pairs > g_max_ctas) pairs = g_max_ctas / 2 > 0 ? g_max_ctas / 2 : 1;
-  gemm2_bf16_kernel<<<2 * pairs, 256, SMEM2_BYTES, st>>>(ma, mb, p);
+  gemm2_bf16_kernel<<<2 * pairs, kThreads2, SMEM2_BYTES, st>>>(maps, p);
   SPMM_CHECK_LAUNCH();
   return 0;
 }
@@ -645,6 +864,11 @@ extern "C" int spmm_gemm_debug_config(int mn_lbo_bytes, int mn_sbo_bytes, int fo
   return 0;
 }
 
+extern "C" int spmm_gemm_debug_trace(void* buf) {
+  g_trace = reinterpret_cast<unsigned long long*>(buf);   // 16 x u64 per CTA; null disables
+  return 0;
+}
+
 extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major,
                               void* C, int ldc, int M, int N, int K, const spmm_gemm_epilogue* epi, void* stream) {
   SPMM_ARG(A && B && C && M > 0 && N > 0 && K > 0);
@@ -659,6 +883,7 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   p.mn_lbo = g_mn_lbo; p.mn_sbo = g_mn_sbo;
   p.debug_nomma = g_nomma;
   p.salt = spmm_g_rng_salt;
+  p.trace = g_trace;
   if (epi) {
     p.bias = epi->bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(epi->residual); p.ldr = epi->ld_residual;
@@ -681,7 +906,15 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   SPMM_ARG(!p.pre || p.ldp % 8 == 0);
   SPMM_ARG(!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
 
-  const bool use2 = g_use_2cta && !g_force_bn && M > BM && N > 128;   // 2-CTA 256x256 pair tiles
+  const bool has_side = p.residual || p.aux;
+  SPMM_ARG(!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+  SPMM_ARG(!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
+  SPMM_ARG(!p.pre || (reinterpret_cast<uintptr_t>(p.pre) & 15) == 0);
+  // 2-CTA 256x256 pair tiles; its staged epilogue has one staging tile, so a side operand excludes f32 / 2nd outputs
+  // (bulk tensor stores were observed to touch the rest of a partially covered 16-byte unit past N, so the 1-CTA
+  // kernel with element-granular stores keeps the ragged-N problems, e.g. the 300-column LM head)
+  const bool use2 = g_use_2cta && !g_force_bn && M > BM && N > 128 && !(has_side && (out_f32 || p.pre)) &&
+                    N % (out_f32 ? 8 : 16) == 0;
   const int bn = use2 ? BN2 : pick_bn(M, N);
   const int slots = use2 ? kNumSMs / 2 : kNumSMs;
   const int tiles_mn = use2 ? ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2) : ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
@@ -703,7 +936,8 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
     p.kb_per_split = (num_kb + best - 1) / best;
     p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
   }
-  CUtensorMap ma, mb;
+  Gemm2Maps maps;
+  CUtensorMap &ma = maps.a, &mb = maps.b;
   int rc;
   if (!p.a_mn) rc = make_map(&ma, A, K, M, lda, BK, BM);
   else rc = make_map(&ma, A, M, K, lda, 64, BK);
@@ -712,6 +946,21 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   else rc = make_map(&mb, B, N, K, ldb, 64, BK);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (use2) return launch2(ma, mb, p, st);
+  if (use2) {
+    // epilogue staging boxes: [128 rows][128 bytes] = 64 bf16 or 32 f32 columns
+    rc = make_map(&maps.c, C, N, M, ldc, out_f32 ? 32 : 64, BM, out_f32);
+    if (rc) return rc;
+    maps.side = maps.c;
+    maps.pre = maps.c;
+    if (has_side) {
+      rc = p.aux ? make_map(&maps.side, p.aux, N, M, p.ldaux, 64, BM) : make_map(&maps.side, p.residual, N, M, p.ldr, 64, BM);
+      if (rc) return rc;
+    }
+    if (p.pre) {
+      rc = make_map(&maps.pre, p.pre, N, M, p.ldp, 64, BM);
+      if (rc) return rc;
+    }
+    return launch2(maps, p, st);
+  }
   return bn == 256 ? launch<256>(ma, mb, p, st) : launch<128>(ma, mb, p, st);
 }

@@ -143,6 +143,58 @@ def test_gemm_epilogues():
     assert rel_err(o1[nz], (ref_pre / 0.9)[nz]) < 6e-3
 
 
+@pytest.mark.parametrize("M,N,K_", [(6144, 3072, 768), (5184, 2304, 768), (6144, 768, 3072), (1000, 300, 768), (390, 520, 136)])
+def test_gemm_epilogues_multi_tile(M, N, K_):
+    """Staged (TMA-store) epilogue of the 2-CTA kernel over several tiles per CTA pair, ragged edges and padded ldc."""
+    a, w = rnd(M, K_, dtype=BF, seed=11), rnd(N, K_, dtype=BF, seed=12, scale=0.05)
+    bias = rnd(N, seed=13)
+    ldc = (N + 63) // 64 * 64
+    ref_pre = a.float() @ w.float().t() + bias
+    res_store = torch.zeros(M, ldc, device=DEV, dtype=BF)
+    res_store[:, :N] = rnd(M, N, dtype=BF, seed=14)
+    res = res_store[:, :N]
+    # bias + dropout + residual into a padded-ld output: pad columns stay untouched
+    out = torch.full((M, ldc), 7.0, device=DEV, dtype=BF)
+    K.gemm(a, w, M, N, K_, bias=bias, residual=res, out=out[:, :N])
+    assert rel_err(out[:, :N], ref_pre + res.float()) < 5e-3
+    if ldc > N:
+        assert float((out[:, N:] - 7.0).abs().max()) == 0.0
+    mk = lambda dt=BF: torch.empty(M, ldc, device=DEV, dtype=dt)[:, :N]    # row stride stays a multiple of 64
+    o1 = K.gemm(a, w, M, N, K_, bias=bias, residual=res, dropout_p=0.1, seed=5, out=mk())
+    d = o1.float() - res.float()
+    nz = d.abs() > 1e-2
+    assert abs(nz.float().mean().item() - 0.9) < 0.02
+    # gelu + pre-activation (two outputs)
+    pre = mk()
+    act = K.gemm(a, w, M, N, K_, bias=bias, gelu=True, pre_act_out=pre, out=mk())
+    assert rel_err(pre, ref_pre) < 5e-3 and rel_err(act, F.gelu(ref_pre)) < 6e-3
+    # dgelu side operand
+    x = mk()
+    x.copy_(rnd(M, N, dtype=BF, seed=17))
+    out = K.gemm(a, w, M, N, K_, dgelu_pre=x, out=mk())
+    xf = x.float().requires_grad_(True)
+    F.gelu(xf).backward((a.float() @ w.float().t()))
+    assert rel_err(out, xf.grad) < 6e-3
+    # fp32 store and fp32 accumulate
+    o32 = K.gemm(a, w, M, N, K_, bias=bias, out_f32=True, out=mk(torch.float32))
+    assert rel_err(o32, ref_pre) < 1e-3
+    acc = mk(torch.float32)
+    acc.copy_(rnd(M, N, seed=18))
+    want = acc + a.float() @ w.float().t()
+    K.gemm(a, w, M, N, K_, out=acc, out_f32=True, accumulate=True)
+    assert rel_err(acc, want) < 1e-3
+
+
+def test_gemm_wgrad_split_k():
+    """dW += dY^T X with both operands MN-major and a long K: split-K partials meet in the f32 reduce-add epilogue."""
+    for (n_out, k_in, tokens) in [(768, 768, 6144), (2304, 768, 5184), (768, 3072, 6144)]:
+        dy, x = rnd(tokens, n_out, dtype=BF, seed=21, scale=0.1), rnd(tokens, k_in, dtype=BF, seed=22)
+        gw = rnd(n_out, k_in, seed=23)
+        want = gw + dy.float().t() @ x.float()
+        K.gemm(dy, x, n_out, k_in, tokens, a_mn=True, b_mn=True, out=gw, out_f32=True, accumulate=True)
+        assert rel_err(gw, want) < 1e-3, (n_out, k_in, rel_err(gw, want))
+
+
 # ---------------------------------------------------------------- LayerNorm
 @pytest.mark.parametrize("rows,H", [(5184, 768), (333, 128), (7, 1024)])
 def test_layernorm_fwd_bwd(rows, H):
