@@ -156,6 +156,25 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def shutdown_distributed(dist, torch, graphed=None):
+    """Leaves the process group without hanging the launcher: CUDA graphs that captured NCCL kernels are released first,
+    and if communicator teardown still blocks (seen at N=2: both ranks parked in destroy_process_group after the result
+    was printed) the process exits anyway once stdout is flushed."""
+    import gc
+    import threading as th
+    if graphed is not None:
+        graphed.graphs.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    t = th.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(timeout=20)
+    if t.is_alive():
+        os._exit(0)
+
+
 def workload_config(args, B, world):
     return {"workload": "SPMM pretrain step, reference config_bert*.json shapes (12L text/fusion + 6L PV encoder, H768), "
                         "batch %d molecules/GPU, %s, 53-dim PV, momentum queue 36864x256, alpha 0.4, train mode (dropout 0.1)"
@@ -263,7 +282,7 @@ def run_ours(args):
                               "graph": graphed is not None,
                               "host_enqueue_ms_per_step": host_ms}), flush=True)
         if world > 1:
-            dist.destroy_process_group()
+            shutdown_distributed(dist, torch, graphed)
         return
 
     # end-to-end through the public API with host batches
@@ -289,7 +308,7 @@ def run_ours(args):
         dist.barrier()
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            shutdown_distributed(dist, torch, graphed)
         return
 
     pk = peaks()
@@ -316,7 +335,7 @@ def run_ours(args):
                                           "oracle/spmm_ref.py on the host cores (%.1f s/step)" % (ms_cpu / 1e3)}
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        shutdown_distributed(dist, torch, graphed)
 
 
 def kernel_rooflines(torch, kernels, model, step_fn, B, world):
@@ -336,15 +355,49 @@ def kernel_rooflines(torch, kernels, model, step_fn, B, world):
             rec[name].append((s, e, work(*a, **k)))
             return r
         return inner
-    kernels.gemm = wrap("gemm", lambda a, b, M, N, K_, **k: 2.0 * M * N * K_)
+    shapes = []
+
+    def gemm_work(a, b, M, N, K_, **k):
+        mode = "+".join(n for n, on in (("f32acc", k.get("accumulate")), ("f32", k.get("out_f32") and not k.get("accumulate")),
+                                        ("bias", k.get("bias") is not None), ("gelu", k.get("gelu")),
+                                        ("pre", k.get("pre_act_out") is not None), ("drop", k.get("dropout_p", 0) > 0),
+                                        ("res", k.get("residual") is not None), ("dgelu", k.get("dgelu_pre") is not None),
+                                        ("amn", k.get("a_mn")), ("bmn", k.get("b_mn"))) if on) or "plain"
+        shapes.append((M, N, K_, mode))
+        return 2.0 * M * N * K_
+    kernels.gemm = wrap("gemm", gemm_work)
     kernels.ema = wrap("ema", lambda p, pm, pb, pmb, mom: 16.0 * p.numel())             # 8 B read + 4 B + 2x2 B written
     kernels.itc = wrap("itc", lambda zp, zt, zpm, ztm, pq, tq, temp, alpha: 2.0 * 2 * pq.numel() * 4)  # fwd + bwd scan of both queues
+    from spmm_b200 import _lib
+    dump = os.environ.get("SPMM_BENCH_GEMM_TABLE")
+    ring = None
+    if dump:
+        ring = torch.zeros(2048 * 148 * 16, dtype=torch.int64, device="cuda")
+        _lib.lib().spmm_gemm_debug_trace_ring(ring.data_ptr(), 2048)
     try:
+        # the host needs ~60 ms to enqueue an eager step: park the GPU behind a spin kernel so the launches queue up and
+        # the events bracket back-to-back kernels, not host gaps
+        torch.cuda._sleep(int(0.12 * 1.9e9))
         step_fn()
         torch.cuda.synchronize()
     finally:
         kernels.gemm, kernels.ema, kernels.itc = orig["gemm"], orig["ema"], orig["itc"]
+        if dump:
+            _lib.lib().spmm_gemm_debug_trace(None)
     tot = {k: (sum(s.elapsed_time(e) for s, e, _ in v), sum(w for _, _, w in v), len(v)) for k, v in rec.items()}
+    if dump:                                   # per-shape table of the step's GEMMs: event time and in-kernel (%globaltimer) time
+        tr = ring.view(2048, 148, 16).cpu()
+        agg = {}
+        for i, ((s_, e_, w_), sh) in enumerate(zip(rec["gemm"], shapes)):
+            a_ = agg.setdefault(sh, [0, 0.0, 0.0, 0.0])
+            t = tr[i % 2048]
+            used = t[:, 0] > 0
+            kus = (int(t[used, 8].max()) - int(t[used, 0].min())) / 1e3 if bool(used.any()) else float("nan")
+            a_[0] += 1; a_[1] += s_.elapsed_time(e_); a_[2] += w_; a_[3] += kus
+        with open(dump, "w") as f:
+            for sh, (n_, ms_, w_, kus) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                f.write("M=%6d N=%5d K=%5d %-30s n=%4d  events %8.3f ms avg %6.1f us %6.1f TF/s | in-kernel avg %6.1f us %6.1f TF/s\n"
+                        % (sh[0], sh[1], sh[2], sh[3], n_, ms_, 1e3 * ms_ / n_, w_ / ms_ / 1e9, kus / n_, w_ / n_ / max(kus / n_, 1e-9) / 1e6))
     g_ms, g_fl, g_n = tot["gemm"]
     ach = g_fl / (g_ms / 1e3) / 1e12
     roof = {"kernel": "gemm_bf16_kernel (tcgen05.mma + TMA, all fwd/dgrad/wgrad GEMMs of one step)", "bound": "tensor",

@@ -52,6 +52,7 @@ int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ld
 int spmm_gemm_debug_config(int mn_lbo_bytes, int mn_sbo_bytes, int force_bn, int max_ctas);
 /* debug: device buffer of 16 x u64 per CTA receiving %globaltimer phase stamps of the next GEMM launches; NULL = off */
 int spmm_gemm_debug_trace(void* buf);
+int spmm_gemm_debug_trace_ring(void* buf, long slots);   /* one 148 x 16 x u64 slot per launch, ring of `slots` */
 
 /* ------------------------------------------------------------------ attention core (xbert.py:305-354)
  * softmax(Q K^T * scale + mask) V per (batch, head), head_dim 64, Tq,Tk <= 128.  q/k/v/o rows are
@@ -106,7 +107,9 @@ int spmm_scatter_add_rows_bf16(void* dst, const int* idx, const void* src, int n
 
 /* ------------------------------------------------------------------ ITC / SPC head (SPMM_models.py:92-131)
  * feats are raw projection outputs z[B,E] (fp32); the kernel L2-normalises (F.normalize, :92,95,101,105),
- * forms the 8 similarity blocks against [own momentum feats | queue] without materialising them, and returns
+ * scans [own momentum feats | queue] twice on the tensor cores (tcgen05 kind::tf32 straight from the fp32 queue,
+ * fp32 accumulate: row LSEs, then O = softmax(S) K, from which loss and gradients follow) without materialising
+ * the 8 similarity blocks, and returns
  * loss_ita, d loss/d z_prop, d loss/d z_text, d loss/d temp, plus the in-batch student sims
  * sim_i2t[B,B], sim_t2i[B,B] (for hard negatives, :157-158) and the normalised momentum feats (for enqueue).
  * Queues are stored key-major [Q][E] (the transpose of the reference's [E][Q] buffers). */

@@ -26,6 +26,7 @@ SIGNATURES = {
     "spmm_gemm_bf16": (i32, [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, C.POINTER(GemmEpilogue), vp]),
     "spmm_gemm_debug_config": (i32, [i32, i32, i32, i32]),
     "spmm_gemm_debug_trace": (i32, [vp]),
+    "spmm_gemm_debug_trace_ring": (i32, [vp, C.c_long]),
     "spmm_attn_fwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, f32, f32, u64, vp]),
     "spmm_attn_bwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32,
                             i32, vp, i32, f32, f32, u64, vp]),
@@ -78,7 +79,7 @@ def lib():
 
 
 # kernels launched per C call (for bench.py's `gpu_launches` claim)
-KERNELS_PER_CALL = {"spmm_itc_fwd_bwd": 5, "spmm_lm_loss_fwd_bwd": 3, "spmm_mpm_loss_fwd_bwd": 3, "spmm_enqueue": 2}
+KERNELS_PER_CALL = {"spmm_itc_fwd_bwd": 6, "spmm_lm_loss_fwd_bwd": 3, "spmm_mpm_loss_fwd_bwd": 3, "spmm_enqueue": 2}
 _launches = 0
 
 

@@ -801,6 +801,7 @@ static int g_max_ctas = 0;
 static int g_split_k = 1;
 static int g_nomma = 0;
 static unsigned long long* g_trace = nullptr;
+static long g_trace_slots = 0, g_trace_next = 0;   // > 0: every launch gets its own 148 x 16 slot (ring)
 
 template <int BN>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
@@ -866,6 +867,13 @@ extern "C" int spmm_gemm_debug_config(int mn_lbo_bytes, int mn_sbo_bytes, int fo
 
 extern "C" int spmm_gemm_debug_trace(void* buf) {
   g_trace = reinterpret_cast<unsigned long long*>(buf);   // 16 x u64 per CTA; null disables
+  g_trace_slots = 0;
+  return 0;
+}
+extern "C" int spmm_gemm_debug_trace_ring(void* buf, long slots) {   // launch i writes slot i % slots (148 x 16 x u64 each)
+  g_trace = reinterpret_cast<unsigned long long*>(buf);
+  g_trace_slots = slots;
+  g_trace_next = 0;
   return 0;
 }
 
@@ -884,6 +892,7 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   p.debug_nomma = g_nomma;
   p.salt = spmm_g_rng_salt;
   p.trace = g_trace;
+  if (g_trace && g_trace_slots > 0) p.trace = g_trace + (size_t)(g_trace_next++ % g_trace_slots) * kNumSMs * 16;
   if (epi) {
     p.bias = epi->bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(epi->residual); p.ldr = epi->ld_residual;

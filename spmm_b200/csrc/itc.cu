@@ -1,232 +1,310 @@
 // Fused contrastive (SPC / ITC) head -- reference SPMM_models.py:92-131 (+ the in-batch sims of :157-158).
 //
-// The reference materialises 8 similarity matrices [B, B+Q] (113 MB at B=96, Q=36864) and ~30 elementwise
-// kernels.  Here the two key sets ([own momentum feats | queue]) are streamed tile by tile; the 8 blocks are
-// formed in registers and reduced immediately, never written to memory:
-//   pass 1  per (row-chunk, key-split) CTA: online-softmax statistics of student and teacher rows
-//   combine LSEs, loss_ita, d/d temp
-//   pass 2  same tiling, G = dL/d sim recomputed from the LSEs, dF += G . keys accumulated in registers
-//   finish  chain rule through F.normalize
-// All arithmetic is fp32 (d/d temp is ill-conditioned in bf16).  Queues are key-major
-// [Q][E] so a key is one contiguous 1 KB row.
+// The reference materialises 8 similarity matrices [B, B+Q] (113 MB at B=96, Q=36864) and ~30 elementwise kernels.
+// Here the head is ONE attention-shaped problem per key set: 4B query rows (2B student + 2B momentum-teacher
+// features) against N = B + Q keys ([own momentum features | momentum queue]), with the keys also acting as values:
+//
+//   pass 1   S = Q K^T / temp on the tensor cores, per-row online (max, sum)               -> LSE of every row
+//   pass 2   S again, P = exp(S - LSE), O = P K on the tensor cores                        -> O_r = sum_j softmax_rj k_j
+//   finish   everything the loss needs is linear in O:  sum_j softmax(s)_rj s_rj = f_r.O_r / temp,
+//            sum_j softmax(m)_rj s_rj = f_r.O_teacher(r) / temp,  dL/df_r = (O_r - alpha O_teacher(r) - (1-alpha) k_r+) / (2B temp)
+//
+// so neither the similarities nor the probabilities are ever written, and student / teacher rows need no pairing
+// inside the scan.  Both GEMMs run as tcgen05.mma kind::tf32 straight from the fp32 queue, accumulators in TMEM.
+// The key tile is the K-major B operand of S (TMA SWIZZLE_128B) and the MN-major B operand of O; MN-major 32-bit
+// operands only exist in the 32-byte-atom swizzle (UMMA layout SWIZZLE_128B_BASE32B = TMA SWIZZLE_128B_ATOM_32B; with
+// the 16-byte-atom layout the MMA was observed to write nothing), so pass 2 fetches every key tile in both forms.
+// TF32 keeps 10 mantissa bits of the operands -- the precision of the reference's fp16-autocast `@` -- and
+// accumulates in fp32; queries and P are rounded to nearest, statistics and the chain rule are fp32.
+// Queues are key-major [Q][E]: a key is one contiguous 1 KB row.
+#include <cuda.h>
+#include <mutex>
+
 #include "common.cuh"
 #include "spmm_b200.h"
 
 namespace spmm {
 
 constexpr int E_ = 256;
-constexpr int TK = 64;     // keys per tile
-constexpr int RP = 32;     // (student, teacher) row pairs per CTA
-constexpr int LDS_ = 260;  // padded smem row (floats): conflict-free LDS.128 across rows
-constexpr int GLD = 65;
-constexpr float NEG_BIG = -1e30f;
+constexpr int IT_TM = 128;                      // query rows per CTA (UMMA M)
+constexpr int IT_TK = 32;                       // keys per tile (UMMA N of S, K extent of O)
+constexpr int IT_KC = E_ / 32;                  // 32-float (128 B) swizzle chunks along E
+constexpr int IT_Q_BYTES = IT_TM * E_ * 4;      // 128 KB resident queries
+constexpr int IT_QCH_BYTES = IT_TM * 128;       // one chunk of the query tile
+constexpr int IT_K_BYTES = IT_TK * E_ * 4;      // 32 KB per key stage
+constexpr int IT_KCH_BYTES = IT_TK * 128;       // one chunk of a key tile
+constexpr int IT_STAGES = 2;
+constexpr int IT_P_BYTES = IT_TM * IT_TK * 4;   // 16 KB probability tile (A operand of O)
+constexpr int IT_SMEM = 1024 + IT_Q_BYTES + IT_STAGES * IT_K_BYTES + 2 * IT_P_BYTES + 256;
+constexpr int IT_THREADS = 192;                 // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 softmax / epilogue
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
 
-struct ItcArgs {
-  const float* feats;  // [4][B][E] normalised: f_prop, f_text, m_prop, m_text
-  const float* queue0; // text queue (key set 0)
-  const float* queue1; // prop queue (key set 1)
-  int B, Q, N, splits, tiles_per_split;
-  const float* temp;  // device scalar (the clamped nn.Parameter)
-  float alpha;
-  float* part;     // [2][splits][2B][6]
-  float* rowstat;  // [2][2B][4]: lse_s, lse_m, unused, unused
-  float* sdiag;    // [2][2B]
-  float* sim_i2t;  // [B][B]
-  float* sim_t2i;  // [B][B]
-  float* dF;       // [2][B][E]: d loss / d f_prop, d f_text
+struct ItcMaps {
+  CUtensorMap q;    // Qm [2 * 4B][E] fp32, box 32 x 128 (query tiles)
+  CUtensorMap h;    // same buffer, box 32 x 32 (own-momentum head keys)
+  CUtensorMap k0;   // text queue [Q][E], box 32 x 32 (key set 0)
+  CUtensorMap k1;   // prop queue (key set 1)
+  CUtensorMap h_mn, k0_mn, k1_mn;   // the same three key sources in the 32-byte-atom swizzle (pass 2, MN-major operand)
 };
 
-__device__ __forceinline__ const float* student_ptr(const ItcArgs& a, int ks, int r) {
-  if (ks == 0) return a.feats + (size_t)r * E_;
-  return r < a.B ? a.feats + (size_t)(a.B + r) * E_ : a.feats + (size_t)(r - a.B) * E_;
+struct ItcArgs {
+  int B, Q, rows;               // rows = 4B query rows per key set
+  int nh, ntiles, tiles_per_split, splits;
+  const float* temp;            // device scalar (the clamped nn.Parameter)
+  float* part;                  // [2][splits][mtiles*128][2]  (max, sum) in log2 units
+  const float* lse;             // [2][mtiles*128]             log2-scaled LSE per row (pass 2)
+  float* oacc;                  // [2][4B][E]                  O accumulated over the key splits
+};
+
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ const float* key_ptr(const ItcArgs& a, int ks, int j) {
-  if (j < a.B) return a.feats + (size_t)((ks == 0 ? 3 : 2) * a.B + j) * E_;
-  return (ks == 0 ? a.queue0 : a.queue1) + (size_t)(j - a.B) * E_;
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// MN-major 32-bit operand: [k rows][128 B of MN], 32-byte units XOR (row & 3)  (layout type 1 = SWIZZLE_128B_BASE32B);
+// LBO = stride between 128-byte MN blocks, SBO = stride between 4-row K groups.
+__device__ __forceinline__ uint64_t umma_smem_desc_mn32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-struct Stat { float mx, sum, w; };
-__device__ __forceinline__ void stat_add(Stat& st, float logit, float weight_val) {
-  if (logit > st.mx) {
-    const float sc = __expf(st.mx - logit);
-    st.sum *= sc; st.w *= sc; st.mx = logit;
-  }
-  const float e = __expf(logit - st.mx);
-  st.sum += e; st.w += e * weight_val;
-}
-__device__ __forceinline__ void stat_merge(Stat& a, const Stat& b) {
-  const float m = fmaxf(a.mx, b.mx);
-  const float sa = __expf(a.mx - m), sb = __expf(b.mx - m);
-  a.sum = a.sum * sa + b.sum * sb; a.w = a.w * sa + b.w * sb; a.mx = m;
-}
+// PASS 1: row statistics.  PASS 2: O = softmax(S) K.
+template <int PASS>
+__global__ void __launch_bounds__(IT_THREADS, 1) itc_scan_kernel(const __grid_constant__ ItcMaps maps, const ItcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + IT_Q_BYTES;
+  uint8_t* sP = sK + IT_STAGES * IT_K_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * IT_P_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // [2]
+  uint64_t* k_empty = bars + 3;       // [2]
+  uint64_t* s_full = bars + 5;        // [2]
+  uint64_t* s_empty = bars + 7;       // [2]
+  uint64_t* p_full = bars + 9;        // [2]
+  uint64_t* p_empty = bars + 11;      // [2]
+  uint64_t* o_full = bars + 13;       // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
-// Computes the 2x2x4 micro-tile of logits for this thread: row pairs {ty, ty+16}, keys {tx + 16*k}.
-__device__ __forceinline__ void micro_dots(const float* sq, const float* sk, int ty, int tx, float (&s)[2][4],
-                                           float (&m)[2][4]) {
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) s[i][k] = m[i][k] = 0.f;
-  const float* qs0 = sq + (ty)*LDS_;
-  const float* qs1 = sq + (ty + 16) * LDS_;
-  const float* qm0 = sq + (RP + ty) * LDS_;
-  const float* qm1 = sq + (RP + ty + 16) * LDS_;
-#pragma unroll 4
-  for (int e = 0; e < E_; e += 4) {
-    const float4 a0 = *reinterpret_cast<const float4*>(qs0 + e), a1 = *reinterpret_cast<const float4*>(qs1 + e);
-    const float4 b0 = *reinterpret_cast<const float4*>(qm0 + e), b1 = *reinterpret_cast<const float4*>(qm1 + e);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4 kv = *reinterpret_cast<const float4*>(sk + (tx + 16 * k) * LDS_ + e);
-      s[0][k] += a0.x * kv.x + a0.y * kv.y + a0.z * kv.z + a0.w * kv.w;
-      s[1][k] += a1.x * kv.x + a1.y * kv.y + a1.z * kv.z + a1.w * kv.w;
-      m[0][k] += b0.x * kv.x + b0.y * kv.y + b0.z * kv.z + b0.w * kv.w;
-      m[1][k] += b1.x * kv.x + b1.y * kv.y + b1.z * kv.z + b1.w * kv.w;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, mt = blockIdx.y, ks = blockIdx.z;
+  const int t0 = split * a.tiles_per_split, t1 = min(a.ntiles, t0 + a.tiles_per_split);
+  const int nt = t1 - t0;
+  constexpr uint32_t TMEM_COLS = (PASS == 1) ? 64 : 512;
+  constexpr uint32_t O_COL = 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.q);
+    tma_prefetch_desc(&maps.h);
+    tma_prefetch_desc(ks ? &maps.k1 : &maps.k0);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 4);
+      mbar_init(&p_full[s], 4);
+      mbar_init(&p_empty[s], 1);
     }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
   }
-}
-
-template <bool GRAD>
-__global__ void __launch_bounds__(256, 1) itc_pass_kernel(const ItcArgs a) {
-  extern __shared__ float smem[];
-  float* sq = smem;                  // [2*RP][LDS_]  students then teachers
-  float* sk = sq + 2 * RP * LDS_;    // [TK][LDS_]
-  float* sg = sk + TK * LDS_;        // [RP][GLD]   (GRAD only)
-  const int n_chunks = (2 * a.B + RP - 1) / RP;
-  const int ks = blockIdx.x / n_chunks, chunk = blockIdx.x % n_chunks;
-  const int split = blockIdx.y;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int r_base = chunk * RP;
-
-  // resident query rows for this CTA
-  for (int i = tid; i < 2 * RP * (E_ / 4); i += 256) {
-    const int row = i / (E_ / 4), c4 = i % (E_ / 4);
-    const int r = r_base + (row % RP);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < 2 * a.B) {
-      const float* src = student_ptr(a, ks, r) + (row >= RP ? (size_t)2 * a.B * E_ : 0);
-      v = *reinterpret_cast<const float4*>(src + c4 * 4);
-    }
-    *reinterpret_cast<float4*>(sq + row * LDS_ + c4 * 4) = v;
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
   }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
 
-  Stat ss[2], sm[2];
-  float lse_s[2], lse_m[2];
-  float acc[8][4];
+  if (nt > 0) {
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer =====================
+      mbar_expect_tx(q_full, IT_Q_BYTES);
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    ss[i] = {NEG_BIG, 0.f, 0.f};
-    sm[i] = {NEG_BIG, 0.f, 0.f};
-    const int r = r_base + ty + 16 * i;
-    lse_s[i] = lse_m[i] = 0.f;
-    if (GRAD && r < 2 * a.B) {
-      lse_s[i] = a.rowstat[((size_t)ks * 2 * a.B + r) * 4 + 0];
-      lse_m[i] = a.rowstat[((size_t)ks * 2 * a.B + r) * 4 + 1];
-    }
-  }
-  if (GRAD) {
+      for (int c = 0; c < IT_KC; ++c) tma_load_2d(sQ + c * IT_QCH_BYTES, &maps.q, q_full, c * 32, ks * a.rows + mt * IT_TM);
+      for (int i = 0; i < nt; ++i) {
+        const int t = t0 + i;
+        const bool head = t < a.nh;
+        const int row = head ? ks * a.rows + 3 * a.B + t * IT_TK : (t - a.nh) * IT_TK;
+        if (PASS == 1) {            // two K-major stages
+          const int st = i & 1;
+          mbar_wait(&k_empty[st], ((i >> 1) & 1) ^ 1);
+          mbar_expect_tx(&k_full[st], IT_K_BYTES);
+          const CUtensorMap* m = head ? &maps.h : (ks ? &maps.k1 : &maps.k0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-  }
-  const float inv_temp = 1.f / __ldg(a.temp);
-  const float gscale = inv_temp / (2.f * a.B);
-  const int tile0 = split * a.tiles_per_split;
-  const int n_tiles = (a.N + TK - 1) / TK;
-  const int tile1 = min(n_tiles, tile0 + a.tiles_per_split);
-
-  for (int tile = tile0; tile < tile1; ++tile) {
-    const int j0 = tile * TK;
-    __syncthreads();  // previous tile fully consumed (and sq visible on first iteration)
-    for (int i = tid; i < TK * (E_ / 4); i += 256) {
-      const int row = i / (E_ / 4), c4 = i % (E_ / 4);
-      const int j = j0 + row;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < a.N) v = __ldg(reinterpret_cast<const float4*>(key_ptr(a, ks, j) + c4 * 4));
-      *reinterpret_cast<float4*>(sk + row * LDS_ + c4 * 4) = v;
-    }
-    __syncthreads();
-    float s[2][4], m[2][4];
-    micro_dots(sq, sk, ty, tx, s, m);
+          for (int c = 0; c < IT_KC; ++c) tma_load_2d(sK + st * IT_K_BYTES + c * IT_KCH_BYTES, m, &k_full[st], c * 32, row);
+        } else {                    // buffer 0: K-major tile for S, buffer 1: MN-major tile for O
+          const CUtensorMap* ma = head ? &maps.h : (ks ? &maps.k1 : &maps.k0);
+          const CUtensorMap* mb = head ? &maps.h_mn : (ks ? &maps.k1_mn : &maps.k0_mn);
+          mbar_wait(&k_empty[0], (i & 1) ^ 1);
+          mbar_expect_tx(&k_full[0], IT_K_BYTES);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int r = r_base + ty + 16 * i;
-      const int b = r < a.B ? r : r - a.B;
+          for (int c = 0; c < IT_KC; ++c) tma_load_2d(sK + c * IT_KCH_BYTES, ma, &k_full[0], c * 32, row);
+          mbar_wait(&k_empty[1], (i & 1) ^ 1);
+          mbar_expect_tx(&k_full[1], IT_K_BYTES);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int j = j0 + tx + 16 * k;
-        const float sv = s[i][k] * inv_temp, mv = m[i][k] * inv_temp;
-        const bool ok = (j < a.N) && (r < 2 * a.B);
-        if (!GRAD) {
-          if (ok) {
-            stat_add(ss[i], sv, sv);   // sum exp(s), sum exp(s) * s
-            stat_add(sm[i], mv, sv);   // sum exp(m), sum exp(m) * s
-            if (j == b) a.sdiag[(size_t)ks * 2 * a.B + r] = sv;
-            if (j < a.B && r < a.B) (ks == 0 ? a.sim_i2t : a.sim_t2i)[(size_t)r * a.B + j] = sv;
+          for (int c = 0; c < IT_KC; ++c) tma_load_2d(sK + IT_K_BYTES + c * IT_KCH_BYTES, mb, &k_full[1], c * 32, row);
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_s = umma_idesc_tf32(IT_TM, IT_TK, 0);
+      constexpr uint32_t idesc_o = umma_idesc_tf32(IT_TM, E_, 1);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aP = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      for (int i = 0; i <= nt; ++i) {
+        if (i < nt) {
+          const int st = i & 1;                       // S accumulator buffer
+          const int kst = (PASS == 1) ? st : 0;       // key buffer holding the K-major tile
+          const uint32_t ph = (i >> 1) & 1;
+          mbar_wait(&k_full[kst], (PASS == 1) ? ph : (uint32_t)(i & 1));
+          mbar_wait(&s_empty[st], ph ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < IT_KC; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_tf32(tmem_base + st * IT_TK, umma_smem_desc(aQ + c * IT_QCH_BYTES + k * 32, 16, 1024),
+                          umma_smem_desc(aK + kst * IT_K_BYTES + c * IT_KCH_BYTES + k * 32, 16, 1024), idesc_s, (c | k) != 0);
+          tc_commit(&s_full[st]);
+          tc_commit(&k_empty[kst]);                   // the K-major tile is free once S is formed
+        }
+        if (PASS == 2 && i > 0) {
+          const int j = i - 1, sj = j & 1;
+          mbar_wait(&p_full[sj], (j >> 1) & 1);
+          mbar_wait(&k_full[1], j & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < IT_TK / 8; ++k)   // 8 keys per MMA = two 4-row swizzle atoms of every E chunk
+            tc_mma_tf32(tmem_base + O_COL, umma_smem_desc(aP + sj * IT_P_BYTES + k * 32, 16, 1024),
+                        umma_smem_desc_mn32(aK + IT_K_BYTES + k * 1024, IT_KCH_BYTES, 512), idesc_o, (j | k) != 0);
+          tc_commit(&k_empty[1]);
+          tc_commit(&p_empty[sj]);
+        }
+      }
+      if (PASS == 2) tc_commit(o_full);
+    } else if (warp >= 2) {
+      // ===================== softmax / epilogue warps: thread = one query row =====================
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      const int gr = mt * IT_TM + r;                        // row within this key set's 4B rows
+      const bool row_ok = gr < a.rows;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const float c2 = LOG2E / __ldg(a.temp);               // logits in log2 units
+      float mx = -INFINITY, sum = 0.f;
+      float lse2 = INFINITY;
+      if (PASS == 2 && row_ok) lse2 = a.lse[(size_t)ks * gridDim.y * IT_TM + gr];
+      for (int i = 0; i < nt; ++i) {
+        const int t = t0 + i, st = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        const int nvalid = (t < a.nh) ? min(IT_TK, a.B - t * IT_TK) : min(IT_TK, a.Q - (t - a.nh) * IT_TK);
+        mbar_wait(&s_full[st], ph);
+        tc_fence_after();
+        uint32_t sr[32];
+        tmem_ld32(lane_addr + st * IT_TK, sr);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[st]);
+        if (PASS == 1) {
+          float tmax = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = (j < nvalid) ? __uint_as_float(sr[j]) * c2 : -INFINITY;
+            sr[j] = __float_as_uint(x);
+            tmax = fmaxf(tmax, x);
           }
+          if (tmax > mx) { sum *= fast_exp2(mx - tmax); mx = tmax; }
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s4[j & 3] += fast_exp2(__uint_as_float(sr[j]) - mx);
+          sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
         } else {
-          float g = 0.f;
-          if (ok) {
-            g = __expf(sv - lse_s[i]) - a.alpha * __expf(mv - lse_m[i]) - ((j == b) ? (1.f - a.alpha) : 0.f);
-            g *= gscale;
+          mbar_wait(&p_empty[st], ph ^ 1);
+          uint8_t* prow = sP + st * IT_P_BYTES + r * 128;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4 pv;
+            float* pp = reinterpret_cast<float*>(&pv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * u + e;
+              pp[e] = (j < nvalid) ? round_tf32(fast_exp2(__uint_as_float(sr[j]) * c2 - lse2)) : 0.f;
+            }
+            *reinterpret_cast<float4*>(prow + ((u ^ (r & 7)) << 4)) = pv;
           }
-          sg[(ty + 16 * i) * GLD + tx + 16 * k] = g;
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[st]);
         }
       }
-    }
-    if (GRAD) {
-      __syncthreads();
-      // dF[r][e] += sum_j G[r][j] * key[j][e];  thread: rows rg*8..+7, columns c4*4..+3
-      const int c4 = tid & 63, rg = tid >> 6;
-#pragma unroll 4
-      for (int j = 0; j < TK; ++j) {
-        const float4 kv = *reinterpret_cast<const float4*>(sk + j * LDS_ + c4 * 4);
+      if (PASS == 1) {
+        if (row_ok) {
+          float* p = a.part + ((((size_t)ks * a.splits + split) * gridDim.y * IT_TM) + gr) * 2;
+          p[0] = mx;
+          p[1] = sum;
+        }
+      } else {
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        float* dst = a.oacc + ((size_t)ks * a.rows + gr) * E_;
+#pragma unroll 1
+        for (int c = 0; c < E_ / 32; ++c) {
+          uint32_t orr[32];
+          tmem_ld32(lane_addr + O_COL + c * 32, orr);
+          tmem_ld_wait();
+          if (row_ok) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float g = sg[(rg * 8 + i) * GLD + j];
-          acc[i][0] += g * kv.x; acc[i][1] += g * kv.y; acc[i][2] += g * kv.z; acc[i][3] += g * kv.w;
+            for (int u = 0; u < 8; ++u)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 32 + 4 * u),
+                           "f"(__uint_as_float(orr[4 * u])), "f"(__uint_as_float(orr[4 * u + 1])),
+                           "f"(__uint_as_float(orr[4 * u + 2])), "f"(__uint_as_float(orr[4 * u + 3])) : "memory");
+          }
         }
       }
     }
   }
-
-  if (!GRAD) {
-    // merge the 16 threads (tx) that share a row
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        Stat t;
-        t.mx = __shfl_xor_sync(0xffffffffu, ss[i].mx, o); t.sum = __shfl_xor_sync(0xffffffffu, ss[i].sum, o);
-        t.w = __shfl_xor_sync(0xffffffffu, ss[i].w, o);
-        stat_merge(ss[i], t);
-        t.mx = __shfl_xor_sync(0xffffffffu, sm[i].mx, o); t.sum = __shfl_xor_sync(0xffffffffu, sm[i].sum, o);
-        t.w = __shfl_xor_sync(0xffffffffu, sm[i].w, o);
-        stat_merge(sm[i], t);
-      }
-      const int r = r_base + ty + 16 * i;
-      if (tx == 0 && r < 2 * a.B) {
-        float* p = a.part + (((size_t)ks * a.splits + split) * 2 * a.B + r) * 6;
-        p[0] = ss[i].mx; p[1] = ss[i].sum; p[2] = ss[i].w; p[3] = sm[i].mx; p[4] = sm[i].sum; p[5] = sm[i].w;
-      }
-    }
-  } else {
-    const int c4 = tid & 63, rg = tid >> 6;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = r_base + rg * 8 + i;
-      if (r >= 2 * a.B) continue;
-      // key set 0: rows [0,B) -> f_prop, [B,2B) -> f_text;  key set 1: rows [0,B) -> f_text, [B,2B) -> f_prop
-      const int b = r < a.B ? r : r - a.B;
-      const int which = (ks == 0) ? (r < a.B ? 0 : 1) : (r < a.B ? 1 : 0);
-      float* d = a.dF + ((size_t)which * a.B + b) * E_ + c4 * 4;
-      atomicAdd(d + 0, acc[i][0]); atomicAdd(d + 1, acc[i][1]); atomicAdd(d + 2, acc[i][2]); atomicAdd(d + 3, acc[i][3]);
-    }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-// F.normalize(z, dim=-1) for the four feature matrices (eps 1e-12); one warp per row
+// F.normalize(z, dim=-1) for the four feature matrices (eps 1e-12); one warp per row.  Writes the exact features
+// (outputs + chain rule) and the two TF32-rounded query matrices Qm[ks] = [student 2B | teacher 2B]:
+//   ks 0 (keys = [m_text | text queue]): f_prop, f_text, m_prop, m_text
+//   ks 1 (keys = [m_prop | prop queue]): f_text, f_prop, m_text, m_prop        (rows 3B..4B of Qm[ks] are the head keys)
 __global__ void itc_normalize_kernel(const float* z0, const float* z1, const float* z2, const float* z3, float* feats,
-                                     float* norms, float* out_m_prop, float* out_m_text, int B) {
+                                     float* norms, float* qm, float* out_m_prop, float* out_m_text, int B) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= 4 * B) return;
   const int which = row / B, b = row % B;
@@ -236,87 +314,176 @@ __global__ void itc_normalize_kernel(const float* z0, const float* z1, const flo
   for (int i = 0; i < 8; ++i) { v[i] = z[lane + 32 * i]; ssq += v[i] * v[i]; }
   const float n = fmaxf(sqrtf(warp_sum(ssq)), 1e-12f);
   if (lane == 0) norms[row] = n;
+  const int slot0 = which, slot1 = which ^ 1;   // position of this matrix inside Qm[0] / Qm[1]
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float f = v[i] / n;
-    feats[(size_t)row * E_ + lane + 32 * i] = f;
-    if (which == 2) out_m_prop[(size_t)b * E_ + lane + 32 * i] = f;
-    if (which == 3) out_m_text[(size_t)b * E_ + lane + 32 * i] = f;
+    const int e = lane + 32 * i;
+    feats[(size_t)row * E_ + e] = f;
+    const float ft = round_tf32(f);
+    qm[((size_t)slot0 * B + b) * E_ + e] = ft;
+    qm[((size_t)(4 + slot1) * B + b) * E_ + e] = ft;
+    if (which == 2) out_m_prop[(size_t)b * E_ + e] = f;
+    if (which == 3) out_m_text[(size_t)b * E_ + e] = f;
   }
 }
 
-// one thread per (key set, row): merge split partials -> LSEs, row loss, row d/dtemp; then block-reduce
-__global__ void itc_combine_kernel(ItcArgs a, float* loss, float* dtemp, float* nan_flag) {
-  __shared__ float sh[32];
-  const int total = 4 * a.B;
-  float l = 0.f, dt = 0.f;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int ks = i / (2 * a.B), r = i % (2 * a.B);
-    Stat s = {NEG_BIG, 0.f, 0.f}, m = {NEG_BIG, 0.f, 0.f};
-    for (int sp = 0; sp < a.splits; ++sp) {
-      const float* p = a.part + (((size_t)ks * a.splits + sp) * 2 * a.B + r) * 6;
-      Stat t1 = {p[0], p[1], p[2]}, t2 = {p[3], p[4], p[5]};
-      stat_merge(s, t1);
-      stat_merge(m, t2);
+// in-batch similarities for the hard-negative sampler (SPMM_models.py:157-158): sim_i2t = f_prop m_text^T / temp,
+// sim_t2i = f_text m_prop^T / temp, exact fp32.  grid (B, 2), one thread per column.
+__global__ void itc_inbatch_kernel(const float* feats, const float* temp, float* sim_i2t, float* sim_t2i, int B) {
+  __shared__ float fq[E_];
+  const int r = blockIdx.x, which = blockIdx.y;
+  const float* f = feats + ((size_t)which * B + r) * E_;
+  for (int e = threadIdx.x; e < E_; e += blockDim.x) fq[e] = f[e];
+  __syncthreads();
+  const float inv_temp = 1.f / __ldg(temp);
+  const float* keys = feats + (size_t)(which == 0 ? 3 : 2) * B * E_;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {
+    const float4* k4 = reinterpret_cast<const float4*>(keys + (size_t)j * E_);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < E_ / 4; ++e) {
+      const float4 kv = __ldg(k4 + e);
+      acc += fq[4 * e] * kv.x + fq[4 * e + 1] * kv.y + fq[4 * e + 2] * kv.z + fq[4 * e + 3] * kv.w;
     }
-    const float lse_s = s.mx + __logf(s.sum), lse_m = m.mx + __logf(m.sum);
-    a.rowstat[(size_t)i * 4 + 0] = lse_s;
-    a.rowstat[(size_t)i * 4 + 1] = lse_m;
-    const float sd = a.sdiag[i];
-    const float teacher_dot = m.w / m.sum;   // sum_j softmax(m)_j * s_j
-    const float student_dot = s.w / s.sum;   // sum_j softmax(s)_j * s_j
-    l += lse_s - a.alpha * teacher_dot - (1.f - a.alpha) * sd;
-    dt += student_dot - a.alpha * teacher_dot - (1.f - a.alpha) * sd;
+    (which == 0 ? sim_i2t : sim_t2i)[(size_t)r * B + j] = acc * inv_temp;
   }
-  l = block_sum(l, sh);
-  dt = block_sum(dt, sh);
+}
+
+// merge the key-split partials: lse2[ks][row] = max + log2(sum)   (log2 units)
+__global__ void itc_combine_kernel(const float* part, float* lse, int splits, int rows_pad, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ks = i / rows_pad, r = i % rows_pad;
+  float mx = -INFINITY, sum = 0.f;
+  for (int sp = 0; sp < splits; ++sp) {
+    const float* p = part + (((size_t)ks * splits + sp) * rows_pad + r) * 2;
+    const float m2 = p[0], s2 = p[1];
+    if (s2 > 0.f) {
+      const float m = fmaxf(mx, m2);
+      sum = sum * exp2f(mx - m) + s2 * exp2f(m2 - m);
+      mx = m;
+    }
+  }
+  lse[i] = mx + log2f(sum);
+}
+
+// Loss, d/d temp and the chain rule through F.normalize.  One block; warp per student feature row (2B rows:
+// f_prop[b], f_text[b]); each row occurs once per key set.
+__global__ void __launch_bounds__(1024) itc_finish_kernel(const float* feats, const float* norms, const float* oacc,
+                                                           const float* lse, const float* temp, float alpha, int B,
+                                                           int rows_pad, float* dz_prop, float* dz_text, float* loss,
+                                                           float* dtemp, float* nan_flag) {
+  __shared__ float sh[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float inv_temp = 1.f / __ldg(temp);
+  const float gscale = inv_temp / (2.f * B);
+  const int rows = 4 * B;
+  float l_acc = 0.f, dt_acc = 0.f;
+  for (int fr = warp; fr < 2 * B; fr += nw) {
+    const int which = fr / B, b = fr % B;       // 0: f_prop[b], 1: f_text[b]
+    float f[8], g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { f[i] = feats[(size_t)fr * E_ + lane + 32 * i]; g[i] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      // key set 0 rows: [f_prop | f_text | m_prop | m_text]; key set 1 rows: [f_text | f_prop | m_text | m_prop]
+      const int r = (which == ks) ? b : B + b;
+      const float* S = oacc + ((size_t)ks * rows + r) * E_;
+      const float* T = oacc + ((size_t)ks * rows + 2 * B + r) * E_;
+      const float* kp = feats + ((size_t)(ks == 0 ? 3 : 2) * B + b) * E_;   // positive key: own momentum twin
+      float ds = 0.f, dt = 0.f, dk = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int e = lane + 32 * i;
+        const float s = S[e], t = T[e], k = kp[e];
+        ds += f[i] * s; dt += f[i] * t; dk += f[i] * k;
+        g[i] += gscale * (s - alpha * t - (1.f - alpha) * k);
+      }
+      ds = warp_sum(ds) * inv_temp; dt = warp_sum(dt) * inv_temp; dk = warp_sum(dk) * inv_temp;
+      const float lse_s = lse[(size_t)ks * rows_pad + r] * LN2;
+      l_acc += lse_s - alpha * dt - (1.f - alpha) * dk;
+      dt_acc += ds - alpha * dt - (1.f - alpha) * dk;
+    }
+    // dz = (g - f (f . g)) / ||z||
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dot += f[i] * g[i];
+    dot = warp_sum(dot);
+    const float inv = 1.f / norms[fr];
+    float* out = (which == 0 ? dz_prop : dz_text) + (size_t)b * E_;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[lane + 32 * i] = (g[i] - f[i] * dot) * inv;
+  }
+  // l_acc / dt_acc are warp-uniform: count each warp once
+  float l = block_sum(lane == 0 ? l_acc : 0.f, sh);
+  float dt = block_sum(lane == 0 ? dt_acc : 0.f, sh);
   if (threadIdx.x == 0) {
-    const float L = l / (2.f * a.B);                 // (sum of 4 row-means) / 2
+    const float L = l / (2.f * B);                  // (sum of 4 row-means) / 2
     *loss = L;
-    *dtemp = -dt / (__ldg(a.temp) * 2.f * a.B);         // d s / d temp = -s / temp
-    if (nan_flag) *nan_flag = (L != L) ? 1.f : 0.f;  // reference NaN guard, SPMM_models.py:132
+    *dtemp = -dt / (__ldg(temp) * 2.f * B);         // d s / d temp = -s / temp
+    if (nan_flag) *nan_flag = (L != L) ? 1.f : 0.f; // reference NaN guard, SPMM_models.py:132
   }
 }
 
-// dz = (dF - f (f . dF)) / ||z||   (backward of F.normalize); one warp per row of the two student matrices
-__global__ void itc_finish_kernel(const float* feats, const float* norms, const float* dF, float* dz_prop,
-                                  float* dz_text, int B) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= 2 * B) return;
-  const float* f = feats + (size_t)row * E_;
-  const float* g = dF + (size_t)row * E_;
-  float fv[8], gv[8], dot = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { fv[i] = f[lane + 32 * i]; gv[i] = g[lane + 32 * i]; dot += fv[i] * gv[i]; }
-  dot = warp_sum(dot);
-  const float inv = 1.f / norms[row];
-  float* out = (row < B ? dz_prop + (size_t)row * E_ : dz_text + (size_t)(row - B) * E_);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) out[lane + 32 * i] = (gv[i] - fv[i] * dot) * inv;
+struct ItcPlan { int mtiles, rows_pad, nh, nq, ntiles, splits, tps; };
+static inline ItcPlan itc_plan(int B, int Q) {
+  ItcPlan p;
+  p.mtiles = (4 * B + IT_TM - 1) / IT_TM;
+  p.rows_pad = p.mtiles * IT_TM;
+  p.nh = (B + IT_TK - 1) / IT_TK;
+  p.nq = (Q + IT_TK - 1) / IT_TK;
+  p.ntiles = p.nh + p.nq;
+  int splits = kNumSMs / (2 * p.mtiles);
+  if (splits < 1) splits = 1;
+  if (splits > p.ntiles) splits = p.ntiles;
+  p.tps = (p.ntiles + splits - 1) / splits;
+  p.splits = (p.ntiles + p.tps - 1) / p.tps;
+  return p;
 }
 
-static inline int itc_splits(int B, int N) {
-  const int n_chunks = (2 * B + RP - 1) / RP;
-  const int n_tiles = (N + TK - 1) / TK;
-  int splits = (2 * kNumSMs + 2 * n_chunks - 1) / (2 * n_chunks);
-  if (splits > n_tiles) splits = n_tiles;
-  if (splits < 1) splits = 1;
-  return splits;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn itc_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+// fp32 [rows][E] row-major, box = 32 floats (128 B, SWIZZLE_128B) x box_rows
+static int itc_map(CUtensorMap* m, const float* ptr, uint64_t rows, uint32_t box_rows, bool atom32 = false) {
+  EncodeTiledFn fn = itc_encode_fn();
+  if (!fn) return -2;
+  cuuint64_t dims[2] = {(cuuint64_t)E_, rows};
+  cuuint64_t strides[1] = {E_ * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -3;
 }
 
 }  // namespace spmm
 using namespace spmm;
 
 extern "C" int64_t spmm_itc_workspace_bytes(int B, int E, int Q) {
-  if (E != E_) return -1;
-  const int splits = itc_splits(B, B + Q);
-  int64_t floats = (int64_t)4 * B * E_      // feats
-                   + 4 * B                  // norms
-                   + (int64_t)2 * splits * 2 * B * 6   // partials
-                   + (int64_t)2 * 2 * B * 4             // rowstat
-                   + 2 * 2 * B                          // sdiag
-                   + (int64_t)2 * B * E_;               // dF
-  return floats * 4 + 256;
+  if (E != E_ || B < 1 || Q < 0) return -1;
+  const ItcPlan p = itc_plan(B, Q);
+  int64_t floats = (int64_t)4 * B * E_                       // feats (exact)
+                   + 4 * B                                   // norms
+                   + (int64_t)2 * 4 * B * E_                 // Qm (TF32-rounded query / head-key matrices)
+                   + (int64_t)2 * p.splits * p.rows_pad * 2  // pass-1 partials
+                   + (int64_t)2 * p.rows_pad                 // lse
+                   + (int64_t)2 * 4 * B * E_;                // O accumulators
+  return floats * 4 + 1024;
 }
 
 extern "C" int spmm_itc_fwd_bwd(const float* z_prop, const float* z_text, const float* z_prop_m, const float* z_text_m,
@@ -324,49 +491,73 @@ extern "C" int spmm_itc_fwd_bwd(const float* z_prop, const float* z_text, const 
                                 float alpha, int B, int E, int Q, float* loss, float* dz_prop, float* dz_text,
                                 float* dtemp, float* sim_i2t, float* sim_t2i, float* feat_prop_m, float* feat_text_m,
                                 float* nan_flag, void* workspace, int64_t workspace_bytes, void* stream) {
-  SPMM_ARG(z_prop && z_text && z_prop_m && z_text_m && prop_queue && text_queue && temp);
+  SPMM_ARG(z_prop && z_text && z_prop_m && z_text_m && temp);
   SPMM_ARG(loss && dz_prop && dz_text && dtemp && sim_i2t && sim_t2i && feat_prop_m && feat_text_m && workspace);
-  SPMM_ARG(E == E_ && B >= 1 && Q >= 0);
+  SPMM_ARG(E == E_ && B >= 1 && Q >= 0 && (Q == 0 || (prop_queue && text_queue)));
   SPMM_ARG(workspace_bytes >= spmm_itc_workspace_bytes(B, E, Q));
+  SPMM_ARG(Q == 0 || (((uintptr_t)prop_queue | (uintptr_t)text_queue) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
-  ItcArgs a{};
+  const ItcPlan pl = itc_plan(B, Q);
   float* w = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
-  const int N = B + Q;
-  const int splits = itc_splits(B, N);
-  const int n_tiles = (N + TK - 1) / TK;
   float* feats = w; w += (size_t)4 * B * E_;
-  float* norms = w; w += 4 * B;
-  a.part = w; w += (size_t)2 * splits * 2 * B * 6;
-  a.rowstat = w; w += (size_t)2 * 2 * B * 4;
-  a.sdiag = w; w += 2 * 2 * B;
-  a.dF = w;
-  a.feats = feats; a.queue0 = text_queue; a.queue1 = prop_queue;
-  a.B = B; a.Q = Q; a.N = N; a.splits = splits; a.tiles_per_split = (n_tiles + splits - 1) / splits;
-  a.alpha = alpha; a.sim_i2t = sim_i2t; a.sim_t2i = sim_t2i;
-  a.temp = temp;
+  float* norms = w; w += (4 * B + 63) / 64 * 64;
+  float* qm = w; w += (size_t)2 * 4 * B * E_;
+  float* part = w; w += (size_t)2 * pl.splits * pl.rows_pad * 2;
+  float* lse = w; w += (size_t)2 * pl.rows_pad;
+  float* oacc = w;
 
-  cudaError_t e = cudaMemsetAsync(a.dF, 0, (size_t)2 * B * E_ * sizeof(float), st);
-  if (e != cudaSuccess) return (int)e;
-  itc_normalize_kernel<<<(4 * B + 7) / 8, 256, 0, st>>>(z_prop, z_text, z_prop_m, z_text_m, feats, norms, feat_prop_m,
-                                                        feat_text_m, B);
-  SPMM_CHECK_LAUNCH();
-  const int n_chunks = (2 * B + RP - 1) / RP;
-  const size_t smem1 = (size_t)(2 * RP + TK) * LDS_ * sizeof(float);
-  const size_t smem2 = smem1 + (size_t)RP * GLD * sizeof(float);
+  ItcMaps maps;
+  int rc = itc_map(&maps.q, qm, (uint64_t)2 * 4 * B, IT_TM);
+  if (rc) return rc;
+  rc = itc_map(&maps.h, qm, (uint64_t)2 * 4 * B, IT_TK);
+  if (rc) return rc;
+  rc = itc_map(&maps.h_mn, qm, (uint64_t)2 * 4 * B, IT_TK, true);
+  if (rc) return rc;
+  if (Q > 0) {
+    rc = itc_map(&maps.k0, text_queue, Q, IT_TK);
+    if (rc) return rc;
+    rc = itc_map(&maps.k1, prop_queue, Q, IT_TK);
+    if (rc) return rc;
+    rc = itc_map(&maps.k0_mn, text_queue, Q, IT_TK, true);
+    if (rc) return rc;
+    rc = itc_map(&maps.k1_mn, prop_queue, Q, IT_TK, true);
+    if (rc) return rc;
+  } else {
+    maps.k0 = maps.h;
+    maps.k1 = maps.h;
+    maps.k0_mn = maps.h_mn;
+    maps.k1_mn = maps.h_mn;
+  }
+  ItcArgs a{};
+  a.B = B; a.Q = Q; a.rows = 4 * B;
+  a.nh = pl.nh; a.ntiles = pl.ntiles; a.tiles_per_split = pl.tps; a.splits = pl.splits;
+  a.temp = temp; a.part = part; a.lse = lse; a.oacc = oacc;
+
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(itc_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    cudaFuncSetAttribute(itc_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    cudaError_t e1 = cudaFuncSetAttribute(itc_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IT_SMEM);
+    cudaError_t e2 = cudaFuncSetAttribute(itc_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IT_SMEM);
+    if (e1 != cudaSuccess) return (int)e1;
+    if (e2 != cudaSuccess) return (int)e2;
     configured = true;
   }
-  dim3 grid(2 * n_chunks, splits);
-  itc_pass_kernel<false><<<grid, 256, smem1, st>>>(a);
+  cudaError_t e = cudaMemsetAsync(oacc, 0, (size_t)2 * 4 * B * E_ * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  itc_normalize_kernel<<<(4 * B + 7) / 8, 256, 0, st>>>(z_prop, z_text, z_prop_m, z_text_m, feats, norms, qm, feat_prop_m,
+                                                        feat_text_m, B);
   SPMM_CHECK_LAUNCH();
-  itc_combine_kernel<<<1, 256, 0, st>>>(a, loss, dtemp, nan_flag);
+  itc_inbatch_kernel<<<dim3(B, 2), 128, 0, st>>>(feats, temp, sim_i2t, sim_t2i, B);
   SPMM_CHECK_LAUNCH();
-  itc_pass_kernel<true><<<grid, 256, smem2, st>>>(a);
+  dim3 grid(pl.splits, pl.mtiles, 2);
+  itc_scan_kernel<1><<<grid, IT_THREADS, IT_SMEM, st>>>(maps, a);
   SPMM_CHECK_LAUNCH();
-  itc_finish_kernel<<<(2 * B + 7) / 8, 256, 0, st>>>(feats, norms, a.dF, dz_prop, dz_text, B);
+  const int total = 2 * pl.rows_pad;
+  itc_combine_kernel<<<(total + 255) / 256, 256, 0, st>>>(part, lse, pl.splits, pl.rows_pad, total);
+  SPMM_CHECK_LAUNCH();
+  itc_scan_kernel<2><<<grid, IT_THREADS, IT_SMEM, st>>>(maps, a);
+  SPMM_CHECK_LAUNCH();
+  itc_finish_kernel<<<1, 1024, 0, st>>>(feats, norms, oacc, lse, temp, alpha, B, pl.rows_pad, dz_prop, dz_text, loss, dtemp,
+                                        nan_flag);
   SPMM_CHECK_LAUNCH();
   return 0;
 }

@@ -306,7 +306,7 @@ def test_attention_kv_broadcast():
 
 
 # ---------------------------------------------------------------- ITC head vs the oracle restatement
-@pytest.mark.parametrize("B,Q", [(8, 96), (96, 36864), (6, 96)])
+@pytest.mark.parametrize("B,Q", [(8, 96), (96, 36864), (6, 96), (40, 1000)])
 def test_itc_matches_oracle(B, Q):
     from oracle import spmm_ref
     E = 256
@@ -321,9 +321,16 @@ def test_itc_matches_oracle(B, Q):
     loss, s_i2t, s_t2i = spmm_ref.itc_loss(F.normalize(zp, dim=-1), F.normalize(zt, dim=-1), F.normalize(z[2], dim=-1),
                                            F.normalize(z[3], dim=-1), pq.t().contiguous(), tq.t().contiguous(), tr, 0.4)
     loss.backward()
-    assert abs(float(out["loss"]) - float(loss)) < 2e-5 * abs(float(loss)) + 1e-5
-    assert rel_err(out["dz_prop"], zp.grad) < 1e-4 and rel_err(out["dz_text"], zt.grad) < 1e-4
-    assert abs(float(out["dtemp"]) - float(tr.grad)) < 1e-3 * abs(float(tr.grad)) + 1e-5
+    # The two scans run on the tensor cores in TF32 (10 operand mantissa bits, the precision of the reference's
+    # fp16-autocast matmul; fp32 accumulate).  A CPU emulation of exactly that rounding against this fp32 oracle gives
+    # |d loss| <= 7e-4, rel-L2(dz) <= 2.5e-4 and rel(d temp) <= 1.9e-3 on these cases; the bounds below are 2-5x that
+    # (the hardware truncates the raw fp32 queue keys to TF32 instead of rounding: logits shrink by ~2.4e-4 relative).
+    print("itc B=%d Q=%d: dloss %.2e  dz %.2e %.2e  dtemp rel %.2e" % (
+        B, Q, abs(float(out["loss"]) - float(loss)), rel_err(out["dz_prop"], zp.grad), rel_err(out["dz_text"], zt.grad),
+        abs(float(out["dtemp"]) - float(tr.grad)) / abs(float(tr.grad))))
+    assert abs(float(out["loss"]) - float(loss)) < 4e-3
+    assert rel_err(out["dz_prop"], zp.grad) < 1e-3 and rel_err(out["dz_text"], zt.grad) < 1e-3
+    assert abs(float(out["dtemp"]) - float(tr.grad)) < 5e-3 * abs(float(tr.grad)) + 1e-5
     assert torch.allclose(out["sim_i2t"], s_i2t[:, :B].detach(), atol=1e-4)
     assert torch.allclose(out["sim_t2i"], s_t2i[:, :B].detach(), atol=1e-4)
     assert torch.allclose(out["feat_prop_m"], F.normalize(z[2], dim=-1), atol=1e-6)
