@@ -63,6 +63,7 @@ int spmm_gemm_debug_trace_ring(void* buf, long slots);   /* one 148 x 16 x u64 s
 int spmm_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                   float* lse, int batch, int heads, int Tq, int Tk, const int* kv_len, int causal,
                   int kv_batch_stride_rows, float scale, float dropout_p, unsigned long long seed, void* stream);
+int spmm_attn_debug_trace(void* buf);   /* debug: 32 x u64 %globaltimer stamps per CTA of the next forward launches */
 int spmm_attn_bwd(const void* d_o, int lddo, const void* q, int ldq, const void* k, int ldk, const void* v,
                   int ldv, const void* o, int ldo, const float* lse, void* dq, int lddq, void* dk, int lddk,
                   void* dv, int lddv, int batch, int heads, int Tq, int Tk, const int* kv_len, int causal,

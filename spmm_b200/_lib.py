@@ -27,6 +27,7 @@ SIGNATURES = {
     "spmm_gemm_debug_config": (i32, [i32, i32, i32, i32]),
     "spmm_gemm_debug_trace": (i32, [vp]),
     "spmm_gemm_debug_trace_ring": (i32, [vp, C.c_long]),
+    "spmm_attn_debug_trace": (i32, [vp]),
     "spmm_attn_fwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, f32, f32, u64, vp]),
     "spmm_attn_bwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32,
                             i32, vp, i32, f32, f32, u64, vp]),

@@ -4,6 +4,8 @@
 // rescale) and the [B,12,Tq,Tk] probability tensor of the reference is never materialised; backward recomputes P
 // from the saved log-sum-exp.  Masks are generated in-kernel from kv_len (pad) and the causal flag.
 // Round-1 MMA path: warp-level mma.sync m16n8k16 bf16 (attention is ~1-2% of step FLOPs).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "spmm_b200.h"
 
@@ -197,14 +199,6 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ dO, int lddo, const __nv_bfloa
   load_tile64(pdO, dO + qrow0 * lddo + h * HD, lddo, Tq, Tq_pad);
   load_tile64(pK, k + krow0 * ldk + h * HD, ldk, Tk, KT);
   load_tile64(pV, v + krow0 * ldv + h * HD, ldv, Tk, KT);
-  // D_i = sum_d dO[i,d] * O[i,d]
-  for (int r = warp; r < Tq; r += nwarps) {
-    float a0, a1, b0, b1;
-    unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dO + (qrow0 + r) * lddo + h * HD + 2 * lane), a0, a1);
-    unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + (qrow0 + r) * ldo + h * HD + 2 * lane), b0, b1);
-    const float d = warp_sum(a0 * b0 + a1 * b1);
-    if (lane == 0) sD[r] = d;
-  }
   __syncthreads();
   const uint32_t sQ = smem_u32(pQ), sdO = smem_u32(pdO), sK = smem_u32(pK), sV = smem_u32(pV), sP = smem_u32(pP),
                  sdS = smem_u32(pdS);
@@ -220,19 +214,41 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ dO, int lddo, const __nv_bfloa
     qk_scores<KT>(sdO, sV, q0, lane, dp);  // dP = dO . V^T has the same operand structure
     const int i0 = q0 + g, i1 = q0 + g + 8;
     const float l0 = i0 < Tq ? lse[(size_t)bh * Tq + i0] : 0.f, l1 = i1 < Tq ? lse[(size_t)bh * Tq + i1] : 0.f;
-    const float d0 = i0 < Tq ? sD[i0] : 0.f, d1 = i1 < Tq ? sD[i1] : 0.f;
+    // pass A: p (in s[]), dropout keep factor folded into dp[], D_i = sum_j (p keep)_ij dP_ij accumulated on the fly
+    // (O = Pd V  =>  sum_d dO_id O_id = sum_j Pd_ij (dO_i . V_j): no second read of O, no serial global-load loop)
+    float d0 = 0.f, d1 = 0.f;
+    uint32_t kept[KT / 64] = {};   // dropout keep bits of this thread's KT/2 elements (one hash per element, reused below)
 #pragma unroll
     for (int n = 0; n < KT / 8; ++n) {
-      float pd[4], ds[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int j = n * 8 + 2 * t + (c & 1), i = (c >> 1) ? i1 : i0;
         const bool ok = (i < Tq) && (j < klen) && (!causal || j <= i);
         const float p = ok ? __expf(s[n][c] * scale - ((c >> 1) ? l1 : l0)) : 0.f;
         float keep = 1.f;
-        if (thresh16) keep = attn_keep(seed, bh, i, j, thresh16) ? inv_keep : 0.f;
+        if (thresh16) {
+          const bool kp = attn_keep(seed, bh, i, j, thresh16);
+          keep = kp ? inv_keep : 0.f;
+          kept[(n * 4 + c) >> 5] |= (kp ? 1u : 0u) << ((n * 4 + c) & 31);
+        }
+        s[n][c] = p;
+        dp[n][c] *= keep;
+        if (c >> 1) d1 += p * dp[n][c]; else d0 += p * dp[n][c];
+      }
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+#pragma unroll
+    for (int n = 0; n < KT / 8; ++n) {
+      float pd[4], ds[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float p = s[n][c];
+        // dp[] already carries keep (= mask / keep_prob): Pd = p * keep needs the factor once more
+        float keep = 1.f;
+        if (thresh16) keep = ((kept[(n * 4 + c) >> 5] >> ((n * 4 + c) & 31)) & 1u) ? inv_keep : 0.f;
         pd[c] = p * keep;
-        ds[c] = p * (dp[n][c] * keep - ((c >> 1) ? d1 : d0));
+        ds[c] = p * (dp[n][c] - ((c >> 1) ? d1 : d0));
       }
       // park bf16 P / dS: element (row, key) -> tile128 chunk key/8, within-chunk offset (key%8)*2 bytes
       const int key = n * 8 + 2 * t;
@@ -314,6 +330,11 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ dO, int lddo, const __nv_bfloa
   }
 }
 
+int attn_fwd_tc_launch(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, float* lse,
+                       int batch, int heads, int Tq, int Tk, const int* kv_len, int causal, int kv_bstride, float scale,
+                       uint32_t thresh16, float inv_keep, unsigned long long seed, cudaStream_t st);   // attention_tc.cu
+void attn_set_trace(void* p);
+
 static inline void attn_drop(float p, uint32_t& th, float& ik) {
   th = p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u;
   ik = p > 0.f ? 1.f / (1.f - p) : 1.f;
@@ -321,6 +342,11 @@ static inline void attn_drop(float p, uint32_t& th, float& ik) {
 
 }  // namespace spmm
 using namespace spmm;
+
+extern "C" int spmm_attn_debug_trace(void* buf) {   /* 32 x u64 per CTA; NULL = off */
+  attn_set_trace(buf);
+  return 0;
+}
 
 extern "C" int spmm_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                              float* lse, int batch, int heads, int Tq, int Tk, const int* kv_len, int causal,
@@ -331,9 +357,13 @@ extern "C" int spmm_attn_fwd(const void* q, int ldq, const void* k, int ldk, con
   SPMM_ARG((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0 && ((uintptr_t)o & 3) == 0);
   uint32_t th; float ik;
   attn_drop(dropout_p, th, ik);
+  cudaStream_t st = (cudaStream_t)stream;
+  SPMM_ARG(ldo % 8 == 0 && ((uintptr_t)o & 15) == 0);
+  if (!getenv("SPMM_ATTN_LEGACY"))
+    return attn_fwd_tc_launch(q, ldq, k, ldk, v, ldv, o, ldo, lse, batch, heads, Tq, Tk, kv_len, causal, kv_batch_stride_rows,
+                              scale, th, ik, seed, st);
   const int KT = Tk <= 64 ? 64 : 128, QT = Tq <= 64 ? 64 : 128;
   dim3 grid(heads, batch);
-  cudaStream_t st = (cudaStream_t)stream;
 #define SPMM_ATTN_FWD(QTV, KTV)                                                                                      \
   {                                                                                                                  \
     constexpr int kSmem = QTV * 128 + 2 * KTV * 128;                                                                 \

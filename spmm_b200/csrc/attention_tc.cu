@@ -1,0 +1,433 @@
+// Fused attention forward on 5th-gen tensor cores (reference xbert.py:305-354: QK^T/8 + additive mask -> softmax ->
+// dropout -> PV; head split/merge permutes :265-268,352-354 folded into the TMA coordinates).
+//
+// Sequences here are short (Tq, Tk <= 128, head_dim 64), so one 128-row UMMA tile holds either one (batch, head)
+// problem or -- when Tq, Tk <= 64 -- a PAIR of heads of the same sample: slot s owns query rows [64s, 64s+64) and key
+// rows [64s, 64s+64) of the tile, S = Q K^T is computed for the whole 128 x 128 tile and only the diagonal blocks are
+// used; P is written block-diagonal so one O = P V chain serves both heads.
+//
+// Persistent CTAs, 576 threads:  warp 0 = TMA producer (3-stage Q/K/V ring), warp 1 = tcgen05.mma issuer (S and O
+// accumulators double-buffered in TMEM), warps 2..17 = softmax: two sets of 8 warps alternate tiles, two threads per
+// query row read its S row from TMEM, mask (kv_len / causal), exponentiate, write bf16 P into the swizzled A-operand
+// tile and later scale the O row (the single-warp-per-scheduler version spent 2.7 us per tile in these warps).
+// The probability tensor of the reference ([B,12,Tq,Tk]) never exists; LSE is saved for backward.
+#include <cuda.h>
+#include <mutex>
+
+#include "common.cuh"
+#include "spmm_b200.h"
+
+namespace spmm {
+
+constexpr int AT_TILE_BYTES = 128 * 128;                 // [128 rows][64 bf16]: Q, K, V tile / one 64-key chunk of P
+constexpr int AT_STAGE_BYTES = 3 * AT_TILE_BYTES;
+constexpr int AT_STAGES = 3;
+constexpr int AT_P_BYTES = 2 * AT_TILE_BYTES;            // P: [128 rows][128 keys] bf16
+constexpr int AT_XCH_BYTES = 2 * 128 * 4 * 4;             // row max / row sum exchange between the two halves of a row
+constexpr int AT_SMEM = 1024 + AT_STAGES * AT_STAGE_BYTES + 2 * AT_P_BYTES + AT_XCH_BYTES + 512;
+constexpr int AT_THREADS = 64 + 512;                      // TMA warp, MMA warp, 16 softmax warps
+constexpr float AT_LOG2E = 1.4426950408889634f;
+constexpr float AT_LN2 = 0.6931471805599453f;
+
+struct AttnMaps {
+  CUtensorMap q, k, v;   // bf16 [rows][heads*64], box 64 x 64, SWIZZLE_128B
+  CUtensorMap o;         // bf16 [batch][Tq][heads*64], box 64 x 64 x 1: rows >= Tq of a sample are clipped by the store
+};
+
+struct AttnFwdArgs {
+  __nv_bfloat16* o;
+  int ldo;
+  float* lse;
+  int batch, heads, Tq, Tk;
+  const int* kv_len;
+  int causal, kv_bstride;
+  float scale;
+  unsigned long long seed;
+  uint32_t thresh16;
+  float inv_keep;
+  const unsigned long long* salt;
+  int pair, hp, num_tiles;
+  unsigned long long* trace;   // debug: 32 x u64 %globaltimer stamps per CTA, null in production
+};
+
+__device__ __forceinline__ void at_mark(const AttnFwdArgs& a, int slot) {
+  if (a.trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[(size_t)blockIdx.x * 32 + slot] = t;
+  }
+}
+
+struct AttnTile { int b, h0, h1, qrow0, qrow1, krow0, krow1; };
+__device__ __forceinline__ AttnTile attn_decode(const AttnFwdArgs& a, int tile) {
+  AttnTile t;
+  if (a.pair) {
+    t.b = tile / a.hp;
+    t.h0 = 2 * (tile % a.hp);
+    t.h1 = min(t.h0 + 1, a.heads - 1);
+    t.qrow0 = t.qrow1 = t.b * a.Tq;
+    t.krow0 = t.krow1 = t.b * a.kv_bstride;
+  } else {
+    t.b = tile / a.heads;
+    t.h0 = t.h1 = tile % a.heads;
+    t.qrow0 = t.b * a.Tq; t.qrow1 = t.qrow0 + 64;
+    t.krow0 = t.b * a.kv_bstride; t.krow1 = t.krow0 + 64;
+  }
+  return t;
+}
+
+__device__ __forceinline__ void bar_sync_at(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void at_tma_store_3d(const void* desc, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ float at_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// dropout keep bits for keys (j, j+1) of query row i of head bh: same function in forward and backward
+__device__ __forceinline__ uint32_t at_drop_bits(uint32_t key, int bh, int i, int j_even) {
+  return drop_bits2(key, ((uint32_t)bh << 14) | ((uint32_t)i << 7) | (uint32_t)j_even);
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnFwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sP = smem + AT_STAGES * AT_STAGE_BYTES;
+  float* xch = reinterpret_cast<float*>(sP + 2 * AT_P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_P_BYTES + AT_XCH_BYTES);
+  uint64_t* full = bars;            // [3] TMA landed
+  uint64_t* empty = bars + 3;       // [3] stage consumed (O MMA done)
+  uint64_t* s_full = bars + 6;      // [2]
+  uint64_t* s_free = bars + 8;      // [2]
+  uint64_t* p_full = bars + 10;     // [2]
+  uint64_t* p_free = bars + 12;     // [2]
+  uint64_t* o_full = bars + 14;     // [2]
+  uint64_t* o_free = bars + 16;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) at_mark(a, 0);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.q);
+    tma_prefetch_desc(&maps.k);
+    tma_prefetch_desc(&maps.v);
+    tma_prefetch_desc(&maps.o);
+    for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 8);
+      mbar_init(&p_full[s], 8); mbar_init(&p_free[s], 1);
+      mbar_init(&o_full[s], 1); mbar_init(&o_free[s], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) at_mark(a, 1);
+  // TMEM columns: S[ab] at 128*ab (128 fp32 columns each), O[ob] at 256 + 64*ob
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int n = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++n) {
+      const int st = n % AT_STAGES;
+      mbar_wait(&empty[st], ((n / AT_STAGES) & 1) ^ 1);
+      const AttnTile t = attn_decode(a, tile);
+      uint8_t* sq = smem + st * AT_STAGE_BYTES;
+      uint8_t* sk = sq + AT_TILE_BYTES;
+      uint8_t* sv = sk + AT_TILE_BYTES;
+      mbar_expect_tx(&full[st], AT_STAGE_BYTES);
+      tma_load_2d(sq, &maps.q, &full[st], t.h0 * 64, t.qrow0);
+      tma_load_2d(sq + AT_TILE_BYTES / 2, &maps.q, &full[st], t.h1 * 64, t.qrow1);
+      tma_load_2d(sk, &maps.k, &full[st], t.h0 * 64, t.krow0);
+      tma_load_2d(sk + AT_TILE_BYTES / 2, &maps.k, &full[st], t.h1 * 64, t.krow1);
+      tma_load_2d(sv, &maps.v, &full[st], t.h0 * 64, t.krow0);
+      tma_load_2d(sv + AT_TILE_BYTES / 2, &maps.v, &full[st], t.h1 * 64, t.krow1);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S = Q K^T: both K-major (head_dim contiguous)
+    const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);    // O = P V: V is [key][d], d contiguous = MN-major B
+    const uint32_t aP = smem_u32(sP);
+    auto issue_o = [&](int m) {
+      const int pb = m & 1, stm = m % AT_STAGES;
+      const uint32_t pph = (m >> 1) & 1;
+      mbar_wait(&p_full[pb], pph);
+      mbar_wait(&o_free[pb], pph ^ 1);
+      tc_fence_after();
+      const uint32_t sv = smem_u32(smem + stm * AT_STAGE_BYTES + 2 * AT_TILE_BYTES);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)   // 16 keys per MMA
+        tc_mma_bf16(tmem_base + 256 + 64 * pb, umma_smem_desc(aP + pb * AT_P_BYTES + (k >> 2) * AT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                    umma_smem_desc(sv + k * 2048, 8192, 1024), idesc_o, k != 0);
+      tc_commit(&o_full[pb]);
+      tc_commit(&empty[stm]);
+      tc_commit(&p_free[pb]);
+    };
+    int n = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++n) {
+      const int st = n % AT_STAGES, ab = n & 1;
+      mbar_wait(&full[st], (n / AT_STAGES) & 1);
+      mbar_wait(&s_free[ab], ((n >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t sq = smem_u32(smem + st * AT_STAGE_BYTES), sk = sq + AT_TILE_BYTES;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        tc_mma_bf16(tmem_base + 128 * ab, umma_smem_desc(sq + k * 32, 16, 1024), umma_smem_desc(sk + k * 32, 16, 1024),
+                    idesc_s, k != 0);
+      tc_commit(&s_full[ab]);
+      if (n > 0) issue_o(n - 1);
+    }
+    if (n > 0) issue_o(n - 1);
+  } else if (warp >= 2) {
+    // ===================== softmax / epilogue =====================
+    // 16 warps = 2 sets x 2 halves x 4 TMEM lane quadrants.  Set g takes the tiles with (n & 1) == g (and the TMEM /
+    // P buffers of that parity); the two threads (half 0 / 1) of a query row split its key columns and its output
+    // columns and exchange row max / row sum through shared memory.
+    const int sw = warp - 2;
+    const int g = sw >> 3, hf = (sw >> 2) & 1, q = warp & 3;
+    const int r = q * 32 + lane;
+    const int bar_id = 1 + g;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t drop_key = a.thresh16 ? fold_seed(salted(a.seed, a.salt)) : 0u;
+    const float c2 = a.scale * AT_LOG2E;
+    const int slot = a.pair ? (r >> 6) : 0;
+    const int i = a.pair ? (r & 63) : r;              // query index within the head
+    const int ncol = a.pair ? 64 : 128;               // columns of S that belong to this row's head
+    const int col0 = a.pair ? 64 * slot : 0;
+    float* xrow = xch + (g * 128 + r) * 4;            // [max half0, max half1, sum half0, sum half1]
+    // carried to the deferred O epilogue of this set's previous tile
+    float prev_inv = 0.f;
+    const bool trw = (warp == 2 && lane == 0);
+
+    AttnTile prev_t{};
+    const bool elected = (hf == 0 && q == 0 && lane == 0);    // issues this set's bulk stores
+    auto epilogue_o = [&](int m) {       // this thread: output columns [32 hf, 32 hf + 32) of its row
+      mbar_wait(&o_full[g], m & 1);        // m = this set's tile counter; P V done => the P buffer is free as well
+      tc_fence_after();
+      uint32_t o0[32];
+      tmem_ld32(lane_addr + 256 + 64 * g + 32 * hf, o0);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[g]);
+      // stage the bf16 O tile ([128 rows][128 B], swizzled) in the first chunk of this set's P buffer, then ONE bulk
+      // tensor store per head: per-thread 16-byte global stores (32 lines per warp instruction) were transaction-bound
+      uint8_t* orow = sP + g * AT_P_BYTES + r * 128;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(o0[8 * u]) * prev_inv, __uint_as_float(o0[8 * u + 1]) * prev_inv);
+        w.y = pack_bf16x2(__uint_as_float(o0[8 * u + 2]) * prev_inv, __uint_as_float(o0[8 * u + 3]) * prev_inv);
+        w.z = pack_bf16x2(__uint_as_float(o0[8 * u + 4]) * prev_inv, __uint_as_float(o0[8 * u + 5]) * prev_inv);
+        w.w = pack_bf16x2(__uint_as_float(o0[8 * u + 6]) * prev_inv, __uint_as_float(o0[8 * u + 7]) * prev_inv);
+        *reinterpret_cast<uint4*>(orow + (((4 * hf + u) ^ (r & 7)) << 4)) = w;
+      }
+      fence_proxy_async();
+      bar_sync_at(bar_id, 256);
+      if (elected) {
+        uint8_t* stg = sP + g * AT_P_BYTES;
+        if (a.pair) {
+          at_tma_store_3d(&maps.o, stg, prev_t.h0 * 64, 0, prev_t.b);
+          if (prev_t.h0 + 1 < a.heads) at_tma_store_3d(&maps.o, stg + AT_TILE_BYTES / 2, (prev_t.h0 + 1) * 64, 0, prev_t.b);
+        } else {
+          at_tma_store_3d(&maps.o, stg, prev_t.h0 * 64, 0, prev_t.b);
+          if (a.Tq > 64) at_tma_store_3d(&maps.o, stg + AT_TILE_BYTES / 2, prev_t.h0 * 64, 64, prev_t.b);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
+
+    int n = 0, nl = 0;   // n: CTA-local tile counter, nl: this set's tile counter
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++n) {
+      if ((n & 1) != g) continue;
+      const bool tr = trw && nl < 4;
+      if (nl > 0) epilogue_o(nl - 1);              // O of this set's previous tile (its P V ran during the other set's tile)
+      const AttnTile t = attn_decode(a, tile);
+      const int h = a.pair ? t.h0 + slot : t.h0;
+      const bool valid = (h < a.heads) && (i < a.Tq);
+      const int klen = a.kv_len ? min(__ldg(a.kv_len + t.b), a.Tk) : a.Tk;
+      const int jmax = a.causal ? min(klen, i + 1) : klen;     // keys [0, jmax) are visible to this row
+      const int bh = t.b * a.heads + h;
+      const uint32_t ph = nl & 1;
+      if (tr) at_mark(a, 4 + 6 * nl);
+      mbar_wait(&s_full[g], ph);
+      tc_fence_after();
+      if (tr) at_mark(a, 5 + 6 * nl);
+      const uint32_t s_addr = lane_addr + 128 * g + col0;
+      // this thread's key chunks (32 columns each) inside the row's head block: cc = 32 hf (+ 64 in single-head mode)
+      // pass 1: row maximum over the visible keys (log2 units)
+      float mx = -INFINITY;
+      for (int cc = 32 * hf; cc < ncol && cc < klen; cc += 64) {     // warp-uniform (tcgen05.ld is warp-collective)
+        uint32_t sr[32];
+        tmem_ld32(s_addr + cc, sr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (cc + j < jmax) mx = fmaxf(mx, __uint_as_float(sr[j]));
+      }
+      xrow[hf] = mx;
+      if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // O staging (= P buffer) drained
+      bar_sync_at(bar_id, 256);
+      mx = fmaxf(xrow[0], xrow[1]);
+      mx = (mx == -INFINITY) ? 0.f : mx * c2;     // fully masked row: p = 0 everywhere, output zeros
+      if (tr) at_mark(a, 6 + 6 * nl);
+      // pass 2: p = exp2(s*c2 - mx), partial row sum, bf16 P (with dropout) into the A-operand tile.  The thread writes
+      // the P columns [32 hf, +32) and [64 + 32 hf, +32) of its row; columns of the other head's block are zeros.
+      mbar_wait(&p_free[g], ph ^ 1);
+      uint8_t* prow = sP + g * AT_P_BYTES + r * 128;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c = 32 * hf; c < 128; c += 64) {
+        const int cc = c - col0;                   // column within this row's head
+        const bool blk = cc >= 0 && cc < ncol && cc < klen;   // warp-uniform: chunk of this warp's head with visible keys
+        uint32_t w[16];
+        if (blk) {
+          uint32_t sr[32];
+          tmem_ld32(s_addr + cc, sr);
+          tmem_ld_wait();
+          float p[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            p[j] = (valid && cc + j < jmax) ? at_exp2(__uint_as_float(sr[j]) * c2 - mx) : 0.f;
+            s4[j & 3] += p[j];
+          }
+          if (a.thresh16) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const uint32_t hb = at_drop_bits(drop_key, bh, i, cc + j);
+              p[j] = ((hb & 0xFFFFu) >= a.thresh16) ? p[j] * a.inv_keep : 0.f;
+              p[j + 1] = ((hb >> 16) >= a.thresh16) ? p[j + 1] * a.inv_keep : 0.f;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(p[2 * j], p[2 * j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = 0u;
+        }
+        uint8_t* chunk = prow + (c >> 6) * AT_TILE_BYTES;   // 64-key chunk of the P tile
+        const int u0 = (c & 63) >> 3;                      // first 16-byte unit (8 keys) inside the chunk row
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(chunk + (((u0 + u) ^ (r & 7)) << 4)) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+      }
+      if (tr) at_mark(a, 7 + 6 * nl);
+      xrow[2 + hf] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&s_free[g]); mbar_arrive(&p_full[g]); }
+      bar_sync_at(bar_id, 256);
+      const float sum = xrow[2] + xrow[3];
+      if (tr) at_mark(a, 8 + 6 * nl);
+      if (valid && hf == 0 && a.lse != nullptr) a.lse[(size_t)bh * a.Tq + i] = (sum > 0.f) ? mx * AT_LN2 + __logf(sum) : 0.f;
+      prev_inv = (valid && sum > 0.f) ? 1.f / sum : 0.f;
+      prev_t = t;
+      if (tr) at_mark(a, 9 + 6 * nl);
+      ++nl;
+    }
+    if (nl > 0) {
+      epilogue_o(nl - 1);
+      if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  }
+  if (threadIdx.x == 64) at_mark(a, 2);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+  if (threadIdx.x == 0) at_mark(a, 3);
+}
+
+typedef CUresult (*AtEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static AtEncodeFn at_encode_fn() {
+  static AtEncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<AtEncodeFn>(f);
+  });
+  return fn;
+}
+// bf16 [rows][cols] with leading dimension ld (elements); box = 64 columns (one head) x 64 rows
+int attn_make_map(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld) {
+  AtEncodeFn fn = at_encode_fn();
+  if (!fn) return -2;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -3;
+}
+
+static unsigned long long* g_attn_trace = nullptr;
+void attn_set_trace(void* p) { g_attn_trace = reinterpret_cast<unsigned long long*>(p); }
+
+// bf16 [batch][T][cols] view of a [batch*T][ld] buffer; box = 64 columns x 64 rows of one sample (rows >= T are clipped)
+int attn_make_map3d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t T, uint64_t batch, uint64_t ld) {
+  AtEncodeFn fn = at_encode_fn();
+  if (!fn) return -2;
+  cuuint64_t dims[3] = {cols, T, batch};
+  cuuint64_t strides[2] = {ld * 2, T * ld * 2};
+  cuuint32_t box[3] = {64, 64, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -3;
+}
+
+int attn_fwd_tc_launch(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, float* lse,
+                       int batch, int heads, int Tq, int Tk, const int* kv_len, int causal, int kv_bstride, float scale,
+                       uint32_t thresh16, float inv_keep, unsigned long long seed, cudaStream_t st) {
+  AttnMaps maps;
+  const uint64_t krows = kv_bstride ? (uint64_t)(batch - 1) * kv_bstride + Tk : (uint64_t)Tk;
+  int rc = attn_make_map(&maps.q, q, (uint64_t)heads * 64, (uint64_t)batch * Tq, ldq);
+  if (rc) return rc;
+  rc = attn_make_map(&maps.k, k, (uint64_t)heads * 64, krows, ldk);
+  if (rc) return rc;
+  rc = attn_make_map(&maps.v, v, (uint64_t)heads * 64, krows, ldv);
+  if (rc) return rc;
+  rc = attn_make_map3d(&maps.o, o, (uint64_t)heads * 64, Tq, batch, ldo);
+  if (rc) return rc;
+  AttnFwdArgs a{};
+  a.o = reinterpret_cast<__nv_bfloat16*>(o); a.ldo = ldo; a.lse = lse;
+  a.batch = batch; a.heads = heads; a.Tq = Tq; a.Tk = Tk; a.kv_len = kv_len; a.causal = causal; a.kv_bstride = kv_bstride;
+  a.scale = scale; a.seed = seed; a.thresh16 = thresh16; a.inv_keep = inv_keep; a.salt = spmm_g_rng_salt;
+  a.pair = (Tq <= 64 && Tk <= 64) ? 1 : 0;
+  a.trace = g_attn_trace;
+  a.hp = (heads + 1) / 2;
+  a.num_tiles = a.pair ? batch * a.hp : batch * heads;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int ctas = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
+  attn_fwd_tc_kernel<<<ctas, AT_THREADS, AT_SMEM, st>>>(maps, a);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace spmm

@@ -10,13 +10,20 @@ BF = torch.bfloat16
 
 
 def timeit(fn, iters=20, warm=3):
+    """Device time per call: the calls are captured into one CUDA graph and replayed, so Python / ctypes / tensor-map
+    encoding on the host does not show up (an eager loop of ~15 us kernels measures the host)."""
     for _ in range(warm):
         fn(0)
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for i in range(iters):
-        fn(i)
+    g.replay()
     e.record()
     torch.cuda.synchronize()
     return s.elapsed_time(e) / iters * 1e3   # us
