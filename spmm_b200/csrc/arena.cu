@@ -118,6 +118,8 @@ __global__ void __launch_bounds__(256) dgelu_kernel(const uint4* __restrict__ da
 // out[c] += sum_r x[r][c]; block = 32x8 threads handles a 256-column x rows_per_block slab
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int ld, float* out, int rows,
                                                      int cols, int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[8][33 * 8];
   const int c0 = blockIdx.x * 256 + threadIdx.x % 32 * 8;
   const int r0 = blockIdx.y * rows_per_block;
@@ -262,9 +264,9 @@ extern "C" int spmm_colsum_bf16(const void* x, int ld, float* out, int rows, int
   if (row_blocks > (rows + 31) / 32) row_blocks = (rows + 31) / 32;
   if (row_blocks < 1) row_blocks = 1;
   const int rpb = (rows + row_blocks - 1) / row_blocks;
-  colsum_kernel<<<dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, out, rows,
-                                                                                cols, rpb);
-  SPMM_CHECK_LAUNCH();
+  cudaError_t le = launch_pdl(colsum_kernel, dim3(col_blocks, row_blocks), dim3(256), 0, (cudaStream_t)stream,
+                              (const __nv_bfloat16*)x, ld, out, rows, cols, rpb);
+  if (le != cudaSuccess) return (int)le;
   return 0;
 }
 

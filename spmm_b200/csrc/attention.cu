@@ -181,6 +181,8 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ dO, int lddo, const __nv_bfloa
                 __nv_bfloat16* __restrict__ dv, int lddv, int heads, int Tq, int Tk, const int* __restrict__ kv_len,
                 int causal, float scale, unsigned long long seed, uint32_t thresh16, float inv_keep,
                 const unsigned long long* salt) {
+  pdl_trigger();
+  pdl_wait();
   if (thresh16) seed = salted(seed, salt);
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* pQ = smem;               // [QT][64]
@@ -401,10 +403,11 @@ extern "C" int spmm_attn_bwd(const void* d_o, int lddo, const void* q, int ldq, 
     constexpr int kSmem = 2 * QTV * 128 + 2 * KTV * 128 + 2 * QTV * KTV * 2 + QTV * 4;                                \
     static bool cfg = false;                                                                                          \
     if (!cfg) { cudaFuncSetAttribute(attn_bwd_kernel<QTV, KTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem); cfg = true; } \
-    attn_bwd_kernel<QTV, KTV><<<grid, QTV * 2, kSmem, st>>>(                                                          \
+    cudaError_t le = launch_pdl(attn_bwd_kernel<QTV, KTV>, grid, dim3(QTV * 2), kSmem, st,                          \
         (const __nv_bfloat16*)d_o, lddo, (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk,                  \
         (const __nv_bfloat16*)v, ldv, (const __nv_bfloat16*)o, ldo, lse, (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, \
         lddk, (__nv_bfloat16*)dv, lddv, heads, Tq, Tk, kv_len, causal, scale, seed, th, ik, spmm_g_rng_salt);         \
+    if (le != cudaSuccess) return (int)le;                                                                            \
   }
   if (QT == 64) SPMM_ATTN_BWD(64, 64) else if (KT == 64) SPMM_ATTN_BWD(128, 64) else SPMM_ATTN_BWD(128, 128)
 #undef SPMM_ATTN_BWD

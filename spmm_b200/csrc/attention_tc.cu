@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
   uint64_t* o_free = bars + 16;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) at_mark(a, 0);
   if (warp == 0 && lane == 0) {
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   if (threadIdx.x == 0) at_mark(a, 1);
   // TMEM columns: S[ab] at 128*ab (128 fp32 columns each), O[ob] at 256 + 64*ob
 
@@ -425,8 +427,8 @@ int attn_fwd_tc_launch(const void* q, int ldq, const void* k, int ldk, const voi
     configured = true;
   }
   const int ctas = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
-  attn_fwd_tc_kernel<<<ctas, AT_THREADS, AT_SMEM, st>>>(maps, a);
-  SPMM_CHECK_LAUNCH();
+  cudaError_t le = launch_pdl(attn_fwd_tc_kernel, dim3(ctas), dim3(AT_THREADS), AT_SMEM, st, maps, a);
+  if (le != cudaSuccess) return (int)le;
   return 0;
 }
 

@@ -23,6 +23,27 @@ namespace spmm {
 
 constexpr int kNumSMs = 148;
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The hot kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel lets its successor
+// start launching right away (pdl_trigger at its top) and waits for its own predecessor to finish and flush
+// (pdl_wait) before its first global-memory access.  Launch latency, barrier/TMEM set-up and descriptor prefetch of
+// kernel N+1 then overlap the tail of kernel N -- a step is ~1600 kernels of 5-60 us.  Both are no-ops when the
+// kernel was launched without the attribute.  SPMM_PDL=0 in the environment turns the attribute off.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();   // misc.cu
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ unsigned long long salted(unsigned long long seed, const unsigned long long* salt) {
   return salt ? seed + __ldg(salt) * 0x9E3779B97F4A7C15ull : seed;
 }

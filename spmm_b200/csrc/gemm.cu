@@ -240,6 +240,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(smem + kStages * Cfg::STAGE_BYTES + 256);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
   const int num_mn = num_m * num_n;
@@ -269,6 +270,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // set-up above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -512,6 +514,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
   float* s_bias = reinterpret_cast<float*>(staging + STG_BYTES + 512);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) trace_mark(p, 0);
   const uint32_t rank = cluster_ctarank();
@@ -554,6 +557,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
   cluster_sync_all();   // peer barriers initialised / TMEM allocated before any cross-CTA traffic
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // set-up above overlapped the previous kernel's tail; its results are visible from here on
   if (threadIdx.x == 0) trace_mark(p, 1);
 
   if (warp == 0 && lane == 0) {
@@ -816,8 +820,8 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.splits;
   int ctas = tiles < kNumSMs ? tiles : kNumSMs;
   if (g_max_ctas > 0 && ctas > g_max_ctas) ctas = g_max_ctas;
-  gemm_bf16_kernel<BN><<<ctas, 256, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
-  SPMM_CHECK_LAUNCH();
+  cudaError_t le = launch_pdl(gemm_bf16_kernel<BN>, dim3(ctas), dim3(256), Cfg::SMEM_BYTES, st, ma, mb, p);
+  if (le != cudaSuccess) return (int)le;
   return 0;
 }
 
@@ -833,8 +837,8 @@ static int launch2(const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st) 
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN2 - 1) / BN2) * p.splits;
   int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
   if (g_max_ctas > 0 && 2 * pairs > g_max_ctas) pairs = g_max_ctas / 2 > 0 ? g_max_ctas / 2 : 1;
-  gemm2_bf16_kernel<<<2 * pairs, kThreads2, SMEM2_BYTES, st>>>(maps, p);
-  SPMM_CHECK_LAUNCH();
+  cudaError_t le = launch_pdl(gemm2_bf16_kernel, dim3(2 * pairs), dim3(kThreads2), SMEM2_BYTES, st, maps, p);
+  if (le != cudaSuccess) return (int)le;
   return 0;
 }
 

@@ -31,6 +31,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
               float eps, unsigned long long seed, uint32_t thresh16, float inv_keep, const unsigned long long* salt) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t key = thresh16 ? fold_seed(salted(seed, salt)) : 0u;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
@@ -92,6 +94,8 @@ ln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
                  __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_branch, int rows, int H,
                  unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep, unsigned long long br_seed,
                  uint32_t br_thresh, float br_inv_keep, const unsigned long long* salt) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t out_key = out_thresh ? fold_seed(salted(out_seed, salt)) : 0u;
   const uint32_t br_key = br_thresh ? fold_seed(salted(br_seed, salt)) : 0u;
   const int lane = threadIdx.x & 31;
@@ -149,6 +153,8 @@ ln_bwd_param_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     const __nv_bfloat16* __restrict__ branch, float* dgamma, float* dbeta, float* dbias, int rows, int H,
                     int rows_per_block, unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep,
                     const unsigned long long* salt) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t out_key = out_thresh ? fold_seed(salted(out_seed, salt)) : 0u;
   __shared__ float sh[3][8][33 * 8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -219,10 +225,11 @@ extern "C" int spmm_layernorm_fwd(const void* x, const float* gamma, const float
   const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   const int nch = (H + 255) / 256;
   cudaStream_t st = (cudaStream_t)stream;
-#define SPMM_LN_FWD(N) ln_fwd_kernel<N><<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, H, eps, seed, th, ik, spmm_g_rng_salt)
+  cudaError_t le = cudaSuccess;
+#define SPMM_LN_FWD(N) le = launch_pdl(ln_fwd_kernel<N>, dim3(grid), dim3(LN_WARPS * 32), 0, st, (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, H, eps, seed, th, ik, spmm_g_rng_salt)
   if (nch == 1) SPMM_LN_FWD(1); else if (nch == 2) SPMM_LN_FWD(2); else if (nch == 3) SPMM_LN_FWD(3); else SPMM_LN_FWD(4);
 #undef SPMM_LN_FWD
-  SPMM_CHECK_LAUNCH();
+  if (le != cudaSuccess) return (int)le;
   return 0;
 }
 
@@ -241,10 +248,11 @@ extern "C" int spmm_layernorm_bwd(const void* dy, const void* x, const float* me
   const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   const int nch = (H + 255) / 256;
   cudaStream_t st = (cudaStream_t)stream;
-#define SPMM_LN_BWD(N) ln_bwd_dx_kernel<N><<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_branch, rows, H, out_seed, oth, oik, branch_seed, bth, bik, spmm_g_rng_salt)
+  cudaError_t le = cudaSuccess;
+#define SPMM_LN_BWD(N) le = launch_pdl(ln_bwd_dx_kernel<N>, dim3(grid), dim3(LN_WARPS * 32), 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_branch, rows, H, out_seed, oth, oik, branch_seed, bth, bik, spmm_g_rng_salt)
   if (nch == 1) SPMM_LN_BWD(1); else if (nch == 2) SPMM_LN_BWD(2); else if (nch == 3) SPMM_LN_BWD(3); else SPMM_LN_BWD(4);
 #undef SPMM_LN_BWD
-  SPMM_CHECK_LAUNCH();
+  if (le != cudaSuccess) return (int)le;
   if (dgamma || dbeta || dbias) {
     const int col_blocks = (H + 255) / 256;
     int row_blocks = (2 * kNumSMs + col_blocks - 1) / col_blocks;
@@ -252,10 +260,10 @@ extern "C" int spmm_layernorm_bwd(const void* dy, const void* x, const float* me
     if (row_blocks < 1) row_blocks = 1;
     const int rpb = (rows + row_blocks - 1) / row_blocks;
     const __nv_bfloat16* branch = (const __nv_bfloat16*)(dx_branch ? dx_branch : dx);
-    ln_bwd_param_kernel<<<dim3(col_blocks, row_blocks), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
-                                                                     mean, rstd, branch, dgamma, dbeta, dbias, rows, H, rpb,
-                                                                     out_seed, oth, oik, spmm_g_rng_salt);
-    SPMM_CHECK_LAUNCH();
+    le = launch_pdl(ln_bwd_param_kernel, dim3(col_blocks, row_blocks), dim3(256), 0, st, (const __nv_bfloat16*)dy,
+                    (const __nv_bfloat16*)x, mean, rstd, branch, dgamma, dbeta, dbias, rows, H, rpb, out_seed, oth, oik,
+                    spmm_g_rng_salt);
+    if (le != cudaSuccess) return (int)le;
   }
   return 0;
 }

@@ -1,4 +1,6 @@
 // Hard-negative sampling (reference SPMM_models.py:154-178) and momentum-queue enqueue (:271-286).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "spmm_b200.h"
 
@@ -90,6 +92,12 @@ __global__ void enqueue_ptr_kernel(int64_t* ptr, int n, int Q, const float* skip
   *ptr = (*ptr + n) % Q;
 }
 
+}  // namespace spmm
+namespace spmm {
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("SPMM_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 }  // namespace spmm
 using namespace spmm;
 
