@@ -32,7 +32,9 @@ enum {
   SPMM_GEMM_OUT_F32 = 1,    /* C is fp32 (default bf16) */
   SPMM_GEMM_ACCUMULATE = 2, /* C += (fp32 only; wgrad accumulation into the flat gradient arena) */
   SPMM_GEMM_GELU = 4,       /* exact-erf GELU (ACT2FN["gelu"], xbert.py:430) after bias */
-  SPMM_GEMM_DGELU = 8       /* multiply by gelu'(dgelu_pre_act) (autograd of xbert.py:436) */
+  SPMM_GEMM_DGELU = 8,      /* multiply by gelu'(dgelu_pre_act) (autograd of xbert.py:436) */
+  SPMM_GEMM_DGELU_STORED = 16 /* with GELU + pre_act: pre_act receives gelu'(pre) (same erf evaluation) instead of pre;
+                                 with DGELU: dgelu_pre_act already holds gelu'(pre), the epilogue only multiplies */
 };
 typedef struct spmm_gemm_epilogue {
   const float* bias;           /* [N] fp32 or NULL */
@@ -152,6 +154,9 @@ int spmm_ema_multi(const float* p, float* p_m, void* p_bf16, void* p_m_bf16, int
                    float one_minus_momentum, void* stream);
 /* clip_grad_norm_(5.) + AdamW (SPMM_models.py:340,361-362).  sumsq_out[0] receives sum g^2. */
 int spmm_grad_sumsq(const float* g, int64_t n, float* sumsq_out, void* stream);
+/* t_dev += 1 (unless *skip_flag != 0) and hyper_dev = {*lr_dev, 1-beta1^t, sqrt(1-beta2^t)} computed on the device */
+int spmm_adam_tick(long long* t_dev, const float* lr_dev, float* hyper_dev, float beta1, float beta2,
+                   const float* skip_flag, void* stream);
 int spmm_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm,
                     float grad_scale, const float* skip_flag, const float* hyper_dev, void* stream);

@@ -18,7 +18,7 @@ class GemmEpilogue(C.Structure):
                 ("dropout_p", f32), ("dropout_seed", u64)]
 
 
-GEMM_OUT_F32, GEMM_ACCUMULATE, GEMM_GELU, GEMM_DGELU = 1, 2, 4, 8
+GEMM_OUT_F32, GEMM_ACCUMULATE, GEMM_GELU, GEMM_DGELU, GEMM_DGELU_STORED = 1, 2, 4, 8, 16
 
 SIGNATURES = {
     "spmm_version": (i32, []),
@@ -55,6 +55,7 @@ SIGNATURES = {
     "spmm_mpm_loss_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "spmm_ema_multi": (i32, [vp, vp, vp, vp, i64, f32, f32, vp]),
     "spmm_grad_sumsq": (i32, [vp, i64, vp, vp]),
+    "spmm_adam_tick": (i32, [vp, vp, vp, f32, f32, vp, vp]),
     "spmm_adamw_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp, vp, vp]),
 }
 
@@ -75,6 +76,8 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get("SPMM_GEMM_DEBUG_FLAGS"):          # debug / A-B runs: e.g. 0x40000 disables the 2-CTA GEMM kernel
+            l.spmm_gemm_debug_config(0, 0, int(os.environ["SPMM_GEMM_DEBUG_FLAGS"], 0), 0)
         _lib = l
     return _lib
 

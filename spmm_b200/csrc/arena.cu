@@ -224,6 +224,27 @@ extern "C" int spmm_grad_sumsq(const float* g, int64_t n, float* sumsq_out, void
   return 0;
 }
 
+// Advances the optimiser's step counter ON THE DEVICE and publishes (lr, 1-beta1^t, sqrt(1-beta2^t)) for adamw_kernel.
+// The counter used to travel host -> pinned -> device per step; a host that enqueues steps ahead of the GPU (or replays
+// a CUDA graph back to back) could overwrite the pinned value before the copy of the previous step had executed.
+__global__ void adam_tick_kernel(long long* t_dev, const float* lr_dev, float* hyper, double beta1, double beta2,
+                                 const float* skip_flag) {
+  if (skip_flag != nullptr && *skip_flag != 0.f) return;   // NaN-guarded step: the reference skips optimizer.step()
+  const long long t = *t_dev + 1;
+  *t_dev = t;
+  hyper[0] = *lr_dev;
+  hyper[1] = (float)(1.0 - pow(beta1, (double)t));
+  hyper[2] = (float)sqrt(1.0 - pow(beta2, (double)t));
+}
+
+extern "C" int spmm_adam_tick(long long* t_dev, const float* lr_dev, float* hyper_dev, float beta1, float beta2,
+                              const float* skip_flag, void* stream) {
+  SPMM_ARG(t_dev && lr_dev && hyper_dev);
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(t_dev, lr_dev, hyper_dev, (double)beta1, (double)beta2, skip_flag);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int spmm_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                                float beta1, float beta2, float eps, float weight_decay, int step, const float* sumsq,
                                float max_norm, float grad_scale, const float* skip_flag, const float* hyper_dev, void* stream) {

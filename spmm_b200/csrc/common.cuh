@@ -209,6 +209,13 @@ __device__ __forceinline__ float fast_erf(float x, float* exp_neg_x2) {
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.f + fast_erf(x * 0.70710678118654752f, nullptr));
 }
+// gelu(x) and gelu'(x) from ONE erf evaluation (the A-S form yields exp(-x^2/2) as a by-product)
+__device__ __forceinline__ float gelu_and_grad(float x, float* grad) {
+  float e;
+  const float cdf = 0.5f * (1.f + fast_erf(x * 0.70710678118654752f, &e));
+  *grad = fmaf(x * 0.3989422804014327f, e, cdf);
+  return x * cdf;
+}
 __device__ __forceinline__ float dgelu_erf(float x) {
   float e;  // exp(-(x/sqrt2)^2) = exp(-x^2/2)
   const float cdf = 0.5f * (1.f + fast_erf(x * 0.70710678118654752f, &e));

@@ -127,23 +127,30 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const int m0,
         v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
       }
     }
+    const bool grad_out = (p.flags & SPMM_GEMM_DGELU_STORED) && do_gelu && p.pre != nullptr;
+    float gr[32];
+    if (grad_out) {   // 2nd output = gelu'(pre) from the same erf evaluation
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float x = v[j]; v[j] = gelu_and_grad(x, &gr[j]); gr[j] = gr[j]; }
+    }
     if (p.pre != nullptr) {
       __nv_bfloat16* pp = p.pre + (size_t)row * p.ldp + col0;
+      const float* pv = grad_out ? gr : v;
       if (full_chunk) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 o;
-          o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-          o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+          o.x = pack_bf16x2(pv[8 * i], pv[8 * i + 1]); o.y = pack_bf16x2(pv[8 * i + 2], pv[8 * i + 3]);
+          o.z = pack_bf16x2(pv[8 * i + 4], pv[8 * i + 5]); o.w = pack_bf16x2(pv[8 * i + 6], pv[8 * i + 7]);
           reinterpret_cast<uint4*>(pp)[i] = o;
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) pp[j] = f2bf(v[j]);
+          if (col0 + j < p.N) pp[j] = f2bf(pv[j]);
       }
     }
-    if (do_gelu) {
+    if (do_gelu && !grad_out) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
     }
@@ -166,7 +173,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const int m0,
 #pragma unroll
         for (int j = 0; j < 32; ++j) s[j] = (col0 + j < p.N) ? bf2f(side[(size_t)row * lds + col0 + j]) : 0.f;
       }
-      if (do_dgelu) {
+      if (do_dgelu && (p.flags & SPMM_GEMM_DGELU_STORED)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= s[j];
+      } else if (do_dgelu) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= dgelu_erf(s[j]);
       } else {
@@ -453,6 +463,19 @@ __device__ __forceinline__ void epi2_chunk(const GemmParams& p, float (&v)[32], 
       v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
     }
   }
+  if (pre_row != nullptr && (p.flags & SPMM_GEMM_DGELU_STORED) && (p.flags & SPMM_GEMM_GELU)) {
+    // 2nd output = gelu'(pre): backward then only multiplies.  One erf evaluation gives both gelu and gelu'.
+    float gr[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_and_grad(v[j], &gr[j]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 o;
+      o.x = pack_bf16x2(gr[8 * i], gr[8 * i + 1]); o.y = pack_bf16x2(gr[8 * i + 2], gr[8 * i + 3]);
+      o.z = pack_bf16x2(gr[8 * i + 4], gr[8 * i + 5]); o.w = pack_bf16x2(gr[8 * i + 6], gr[8 * i + 7]);
+      *reinterpret_cast<uint4*>(pre_row + (((u0 + i) ^ sw) << 4)) = o;
+    }
+  } else {
   if (pre_row != nullptr) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -466,6 +489,7 @@ __device__ __forceinline__ void epi2_chunk(const GemmParams& p, float (&v)[32], 
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
   }
+  }
   if (p.drop_thresh16 != 0) {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {   // element index row*N + col is even here (N % 8 == 0, col0 % 32 == 0)
@@ -474,15 +498,20 @@ __device__ __forceinline__ void epi2_chunk(const GemmParams& p, float (&v)[32], 
     }
   }
   if (has_side) {   // bf16 side operand sits where the result goes
-    const bool do_dgelu = p.flags & SPMM_GEMM_DGELU;
+    const bool do_dgelu = p.flags & SPMM_GEMM_DGELU, stored = p.flags & SPMM_GEMM_DGELU_STORED;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint4 sv = *reinterpret_cast<const uint4*>(out_row + (((u0 + i) ^ sw) << 4));
       float s[8];
       unpack_bf16x2(sv.x, s[0], s[1]); unpack_bf16x2(sv.y, s[2], s[3]);
       unpack_bf16x2(sv.z, s[4], s[5]); unpack_bf16x2(sv.w, s[6], s[7]);
+      if (do_dgelu && stored) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[8 * i + j] = do_dgelu ? v[8 * i + j] * dgelu_erf(s[j]) : v[8 * i + j] + s[j];
+        for (int j = 0; j < 8; ++j) v[8 * i + j] *= s[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * i + j] = do_dgelu ? v[8 * i + j] * dgelu_erf(s[j]) : v[8 * i + j] + s[j];
+      }
     }
   }
   if (out_f32) {

@@ -351,10 +351,11 @@ __global__ void itc_inbatch_kernel(const float* feats, const float* temp, float*
 }
 
 // merge the key-split partials: lse2[ks][row] = max + log2(sum)   (log2 units)
-__global__ void itc_combine_kernel(const float* part, float* lse, int splits, int rows_pad, int total) {
+__global__ void itc_combine_kernel(const float* part, float* lse, int splits, int rows_pad, int rows, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int ks = i / rows_pad, r = i % rows_pad;
+  if (r >= rows) { lse[i] = 0.f; return; }   // padding rows of the last query tile: never written by pass 1
   float mx = -INFINITY, sum = 0.f;
   for (int sp = 0; sp < splits; ++sp) {
     const float* p = part + (((size_t)ks * splits + sp) * rows_pad + r) * 2;
@@ -552,7 +553,7 @@ extern "C" int spmm_itc_fwd_bwd(const float* z_prop, const float* z_text, const 
   itc_scan_kernel<1><<<grid, IT_THREADS, IT_SMEM, st>>>(maps, a);
   SPMM_CHECK_LAUNCH();
   const int total = 2 * pl.rows_pad;
-  itc_combine_kernel<<<(total + 255) / 256, 256, 0, st>>>(part, lse, pl.splits, pl.rows_pad, total);
+  itc_combine_kernel<<<(total + 255) / 256, 256, 0, st>>>(part, lse, pl.splits, pl.rows_pad, 4 * B, total);
   SPMM_CHECK_LAUNCH();
   itc_scan_kernel<2><<<grid, IT_THREADS, IT_SMEM, st>>>(maps, a);
   SPMM_CHECK_LAUNCH();

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import GEMM_ACCUMULATE, GEMM_DGELU, GEMM_GELU, GEMM_OUT_F32, GemmEpilogue, call
+from ._lib import GEMM_ACCUMULATE, GEMM_DGELU, GEMM_DGELU_STORED, GEMM_GELU, GEMM_OUT_F32, GemmEpilogue, call
 
 BF16 = torch.bfloat16
 
@@ -28,7 +28,8 @@ def _chk_cuda(*ts):
 
 
 def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, out=None, out_f32=False, accumulate=False, bias=None,
-         residual=None, pre_act_out=None, dgelu_pre=None, gelu=False, dropout_p=0.0, seed=0, ldc=None):
+         residual=None, pre_act_out=None, dgelu_pre=None, gelu=False, dropout_p=0.0, seed=0, ldc=None,
+         dgelu_stored=False):
     """C[M,N] (+)= epi(A.B^T).  a: [M,K] (K-major) or [K,M] (a_mn); b: [N,K] or [K,N] (b_mn); row stride = ld."""
     _chk_cuda(a, b)
     assert a.dtype == BF16 and b.dtype == BF16 and a.stride(-1) == 1 and b.stride(-1) == 1
@@ -36,7 +37,7 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, out=None, out_f32=False, accu
         out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_f32 else BF16)
     assert out.stride(-1) == 1
     flags = (GEMM_OUT_F32 if out_f32 else 0) | (GEMM_ACCUMULATE if accumulate else 0) | (GEMM_GELU if gelu else 0) | \
-            (GEMM_DGELU if dgelu_pre is not None else 0)
+            (GEMM_DGELU if dgelu_pre is not None else 0) | (GEMM_DGELU_STORED if dgelu_stored else 0)
     epi = GemmEpilogue(_p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
                        _p(pre_act_out), pre_act_out.stride(0) if pre_act_out is not None else 0,
                        _p(dgelu_pre), dgelu_pre.stride(0) if dgelu_pre is not None else 0,
@@ -197,6 +198,11 @@ def mpm_loss(t, w, b, pv, mpm_mask, dw, db):
 
 def grad_sumsq(g, out):
     call("spmm_grad_sumsq", g.data_ptr(), g.numel(), out.data_ptr(), _st())
+
+
+def adam_tick(t_dev, lr_dev, hyper_dev, beta1, beta2, skip_flag=None):
+    call("spmm_adam_tick", t_dev.data_ptr(), lr_dev.data_ptr(), hyper_dev.data_ptr(), float(beta1), float(beta2),
+         _p(skip_flag), _st())
 
 
 def adamw(p, g, m1, m2, lr, beta1, beta2, eps, wd, step, sumsq=None, max_norm=0.0, grad_scale=1.0, skip_flag=None,

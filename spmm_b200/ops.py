@@ -19,6 +19,8 @@ has no fallback.
 import math
 from types import SimpleNamespace
 
+import os
+
 import torch
 
 from . import kernels as K
@@ -42,8 +44,8 @@ class StepRng:
     """Per-training-step randomness that survives CUDA-graph replay.
 
     Per-op seeds (`next_seed()`) are host integers and get baked into a captured graph; the kernels therefore add a
-    DEVICE scalar ("salt") to every seed.  `advance()` bumps the salt in pinned host memory and enqueues a
-    pinned->device copy on the current stream: captured once, the copy node re-reads the host value on every replay.
+    DEVICE scalar ("salt") to every seed.  `advance()` increments the salt ON THE DEVICE (a captured graph replays the
+    increment), so a host that enqueues steps ahead of the GPU cannot make two steps share a salt; `host` mirrors it.
     """
 
     def __init__(self, device):
@@ -53,9 +55,14 @@ class StepRng:
         self.dev = torch.zeros(1, dtype=torch.int64, device=device)
         K.set_rng_salt(self.dev)
 
-    def advance(self):
-        self.host += 1
-        self.dev.copy_(self.host, non_blocking=True)
+    def advance(self, bump_host=True):
+        if bump_host:
+            self.host += 1
+        self.dev.add_(1)
+
+    def reset(self, value=0):
+        self.host.fill_(value)
+        self.dev.fill_(value)
 
 
 _step_rngs = {}
@@ -63,6 +70,8 @@ _step_rngs = {}
 
 def step_rng(device):
     device = torch.device(device)
+    if device.type == "cuda" and device.index is None:      # "cuda" and "cuda:0" must name the same generator
+        device = torch.device("cuda", torch.cuda.current_device())
     r = _step_rngs.get(device)
     if r is None:
         r = _step_rngs[device] = StepRng(device)
@@ -144,6 +153,9 @@ def attn_block(x, enc, W, geom, p_attn, p_hid, anchor):
 
 
 # --------------------------------------------------------------------------------------------- FFN block
+_DGELU_STORED = os.environ.get("SPMM_DGELU_STORED", "1") != "0"
+
+
 class _FfnBlock(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, anchor, W, p_hid):
@@ -151,7 +163,8 @@ class _FfnBlock(torch.autograd.Function):
         M, H = x.shape
         I = W.w1.shape[0]
         pre = torch.empty(M, I, device=x.device, dtype=BF16) if need else None
-        act = K.gemm(x, W.w1, M, I, H, bias=W.b1, gelu=True, pre_act_out=pre)
+        # `pre` receives gelu'(x W1^T + b1) (same erf evaluation as the activation): backward only multiplies
+        act = K.gemm(x, W.w1, M, I, H, bias=W.b1, gelu=True, pre_act_out=pre, dgelu_stored=_DGELU_STORED)
         seed_h = next_seed() if p_hid > 0 else 0
         xsum = K.gemm(act, W.w2, M, H, I, bias=W.b2, residual=x, dropout_p=p_hid, seed=seed_h)
         y, mean, rstd = K.layernorm_fwd(xsum, W.ln_g, W.ln_b, W.eps, save_stats=need)
@@ -170,7 +183,7 @@ class _FfnBlock(torch.autograd.Function):
         dxs, dxb = K.layernorm_bwd(dy.contiguous(), xsum, mean, rstd, W.ln_g, W.g_ln_g, W.g_ln_b, dbias=W.g_b2,
                                    want_branch=True, branch_dropout_p=p_hid, branch_seed=seed_h)
         _wgrad(dxb, act, W.g_w2, H, I, M)
-        dpre = K.gemm(dxb, W.w2, M, I, H, b_mn=True, dgelu_pre=pre)       # (dxb . W2) * gelu'(pre)
+        dpre = K.gemm(dxb, W.w2, M, I, H, b_mn=True, dgelu_pre=pre, dgelu_stored=_DGELU_STORED)   # (dxb . W2) * gelu'(pre)
         K.colsum(dpre, W.g_b1)
         _wgrad(dpre, x, W.g_w1, I, H, M)
         dx = K.gemm(dpre, W.w1, M, H, I, b_mn=True, residual=dxs)

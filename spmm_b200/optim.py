@@ -21,9 +21,13 @@ class FusedClipAdamW(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros(n, device=self.A.device, dtype=torch.float32)
         self.max_norm = max_norm
         self.t = 0
-        # per-step scalars (lr, 1-beta1^t, sqrt(1-beta2^t)) travel through pinned host memory -> device so that a
-        # captured CUDA graph of the step picks up fresh values on every replay
-        self.hyper_host = torch.zeros(3, dtype=torch.float32).pin_memory()
+        # The step counter lives on the device (t_dev, advanced by a 1-thread kernel that also derives the bias
+        # corrections), so a captured CUDA graph of the step picks up fresh values on every replay and a host that runs
+        # ahead of the GPU cannot race the per-step scalars.  Only lr comes from the host (scheduler), through pinned
+        # memory; `t` is the host-side mirror (state_dict, schedulers).
+        self.lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=self.A.device)
+        self.t_dev = torch.zeros(1, dtype=torch.int64, device=self.A.device)
         self.hyper_dev = torch.zeros(3, dtype=torch.float32, device=self.A.device)
 
     def zero_grad(self, set_to_none=False):
@@ -31,14 +35,11 @@ class FusedClipAdamW(torch.optim.Optimizer):
         self.A.zero_grad()
 
     def prepare_step(self):
-        """Host side of a step: advance t and publish (lr, bias corrections) to pinned memory.  Called once per step
+        """Host side of a step: advance the host mirror of t and publish lr to pinned memory.  Called once per step
         BEFORE the (possibly graph-replayed) device work."""
         grp = self.param_groups[0]
         self.t += 1
-        b1, b2 = grp["betas"]
-        self.hyper_host[0] = grp["lr"]
-        self.hyper_host[1] = 1.0 - b1 ** self.t
-        self.hyper_host[2] = (1.0 - b2 ** self.t) ** 0.5
+        self.lr_host[0] = grp["lr"]
 
     @torch.no_grad()
     def step(self, closure=None, skip_flag=None, grad_scale=1.0, prepared=False):
@@ -46,7 +47,8 @@ class FusedClipAdamW(torch.optim.Optimizer):
         grp = self.param_groups[0]
         if not prepared:
             self.prepare_step()
-        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
+        self.lr_dev.copy_(self.lr_host, non_blocking=True)
+        K.adam_tick(self.t_dev, self.lr_dev, self.hyper_dev, grp["betas"][0], grp["betas"][1], skip_flag)
         K.grad_sumsq(A.G[g0:], A.sumsq)
         K.adamw(A.P[g0:], A.G[g0:], self.exp_avg, self.exp_avg_sq, grp["lr"], grp["betas"][0], grp["betas"][1], grp["eps"],
                 grp["weight_decay"], max(self.t, 1), sumsq=A.sumsq, max_norm=self.max_norm, grad_scale=grad_scale,
@@ -57,11 +59,12 @@ class FusedClipAdamW(torch.optim.Optimizer):
         return self.A.sumsq.sqrt() * grad_scale
 
     def state_dict(self):
-        return {"t": self.t, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+        return {"t": int(self.t_dev), "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
                 "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
 
     def load_state_dict(self, sd):
         self.t = sd["t"]
+        self.t_dev.fill_(sd["t"])
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         for g, s in zip(self.param_groups, sd["param_groups"]):

@@ -16,10 +16,7 @@ def train_step(model, optimizer, prop, text_input_ids, text_attention_mask, alph
     """zero_grad -> forward -> backward -> grad all-reduce -> clip(5.) + AdamW.  Returns the 4 losses (device)."""
     from . import ops
     rng = ops.step_rng(model.arena().device)
-    if not _prepared:
-        rng.advance()                       # fresh dropout / sampler randomness for this step
-    else:
-        rng.dev.copy_(rng.host, non_blocking=True)
+    rng.advance(bump_host=not _prepared)    # fresh dropout / sampler randomness for this step (device-side increment)
     optimizer.zero_grad()
     losses = model(prop, text_input_ids, text_attention_mask, alpha=alpha, **fwd_kw)
     loss = losses[0] + losses[1] + losses[2] + losses[3]
@@ -41,8 +38,8 @@ class GraphedTrainStep:
     Python / launch overhead (the eager step spends ~56 ms of host time enqueuing 61 ms of GPU work).
 
     Possible because the step has no host sync: negatives are sampled on the device, queue_ptr and the NaN guard live on
-    the device, and everything that changes per step (dropout / sampler salt, lr, Adam bias corrections) reaches the
-    kernels through pinned-host -> device copies that are part of the graph.  New batches are copied into static input
+    the device, and everything that changes per step lives there too: the dropout / sampler salt and Adam's step
+    counter (with its bias corrections) are advanced by kernels inside the graph; only lr is copied from pinned memory.  New batches are copied into static input
     buffers.  `alpha` is baked into a graph; a new value (epoch-0 ramp, SPMM_models.py:355) captures another graph or,
     with `max_graphs` exceeded, falls back to the eager step.
     """
@@ -56,6 +53,7 @@ class GraphedTrainStep:
         m, o, A = self.model, self.opt, self.model.arena()
         from . import ops
         return {"P": A.P.clone(), "M": A.M.clone(), "m1": o.exp_avg.clone(), "m2": o.exp_avg_sq.clone(), "t": o.t,
+                "t_dev": o.t_dev.clone(),
                 "pq": m.prop_queue_km.clone(), "tq": m.text_queue_km.clone(), "ptr": m.queue_ptr.clone(),
                 "salt": int(ops.step_rng(A.device).host), "rng": torch.cuda.get_rng_state(A.device)}
 
@@ -63,8 +61,9 @@ class GraphedTrainStep:
         m, o, A = self.model, self.opt, self.model.arena()
         from . import ops
         A.P.copy_(s["P"]); A.M.copy_(s["M"]); o.exp_avg.copy_(s["m1"]); o.exp_avg_sq.copy_(s["m2"]); o.t = s["t"]
+        o.t_dev.copy_(s["t_dev"])
         m.prop_queue_km.copy_(s["pq"]); m.text_queue_km.copy_(s["tq"]); m.queue_ptr.copy_(s["ptr"])
-        ops.step_rng(A.device).host.fill_(s["salt"])
+        ops.step_rng(A.device).reset(s["salt"])
         torch.cuda.set_rng_state(s["rng"], A.device)
 
     def _capture(self, key, prop, ids, mask, alpha, mpm_mask):

