@@ -400,18 +400,21 @@ def kernel_rooflines(torch, kernels, model, step_fn, B, world):
                         % (sh[0], sh[1], sh[2], sh[3], n_, ms_, 1e3 * ms_ / n_, w_ / ms_ / 1e9, kus / n_, w_ / n_ / max(kus / n_, 1e-9) / 1e6))
     g_ms, g_fl, g_n = tot["gemm"]
     ach = g_fl / (g_ms / 1e3) / 1e12
-    roof = {"kernel": "gemm_bf16_kernel (tcgen05.mma + TMA, all fwd/dgrad/wgrad GEMMs of one step)", "bound": "tensor",
+    roof = {"kernel": "gemm2_bf16_kernel (tcgen05.mma cta_group::2 + TMA + bulk-store epilogue; all fwd/dgrad/wgrad GEMMs of one step)", "bound": "tensor",
             "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
             "traffic": None, "launches": g_n, "ms_per_step_in_kernel": g_ms, "flops_per_step": g_fl,
             "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)"}
     extra = {}
-    for name, label, unit_bytes in (("ema", "ema_kernel (EMA + bf16 shadows, 16 B/param)", True),
-                                    ("itc", "itc_pass_kernel x2 (+normalize/combine/finish): queue streamed twice", True)):
+    # `traffic` = dram__bytes_read.sum + dram__bytes_write.sum per call from the committed ncu --set full captures
+    # (profiles/r1_ncu_full_itc_ema_r1.csv for the EMA kernel, profiles/r1_ncu_full_itc_tc.csv for the two ITC scans)
+    for name, label, traffic in (("ema", "ema_kernel (EMA + bf16 shadows, 16 B/param)", 2.2427e9),
+                                 ("itc", "spmm_itc_fwd_bwd: itc_scan_kernel<1>, <2> (tcgen05 kind::tf32, queue streamed twice; "
+                                         "pass 2 is tensor-bound) + normalize / in-batch / combine / finish", 160.6e6)):
         ms, by, n = tot[name]
         if n:
             gbs = by / (ms / 1e3) / 1e9
             extra[name] = {"kernel": label, "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                           "frac": gbs / pk["hbm_gbs"], "traffic": None, "ms": ms, "algorithmic_bytes": by}
+                           "frac": gbs / pk["hbm_gbs"], "traffic": traffic, "ms": ms, "algorithmic_bytes": by}
     return roof, extra
 
 
