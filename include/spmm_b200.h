@@ -122,6 +122,7 @@ int spmm_itc_fwd_bwd(const float* z_prop, const float* z_text, const float* z_pr
                      float* feat_prop_m, float* feat_text_m, float* nan_flag, void* workspace, int64_t workspace_bytes,
                      void* stream);
 int64_t spmm_itc_workspace_bytes(int B, int E, int Q);
+int spmm_itc_debug_trace(void* buf);   /* debug: 64 x u64 %globaltimer stamps of one CTA of the pass-1 kernel */
 
 /* hard-negative sampling (SPMM_models.py:154-178): w = softmax(sim[:, :B]) with zero diagonal,
  * idx[b] = argmax_j w[b][j] / Exp(1)  (ATen multinomial n=1 formulation) with a counter-based generator:

@@ -47,6 +47,7 @@ SIGNATURES = {
     "spmm_scatter_add_rows_bf16": (i32, [vp, vp, vp, i32, i64, vp]),
     "spmm_itc_fwd_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                i64, vp]),
+    "spmm_itc_debug_trace": (i32, [vp]),
     "spmm_itc_workspace_bytes": (i64, [i32, i32, i32]),
     "spmm_sample_negatives": (i32, [vp, vp, i32, u64, u64, vp, vp, vp]),
     "spmm_enqueue": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]),

@@ -19,6 +19,7 @@
 // Queues are key-major [Q][E]: a key is one contiguous 1 KB row.
 #include <cuda.h>
 #include <mutex>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "spmm_b200.h"
@@ -55,7 +56,15 @@ struct ItcArgs {
   float* part;                  // [2][splits][mtiles*128][2]  (max, sum) in log2 units
   const float* lse;             // [2][mtiles*128]             log2-scaled LSE per row (pass 2)
   float* oacc;                  // [2][4B][E]                  O accumulated over the key splits
+  unsigned long long* trace;    // debug: 64 x u64 %globaltimer stamps written by CTA (0,0,0); null in production
 };
+__device__ __forceinline__ void it_mark(const ItcArgs& a, int slot) {
+  if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[slot] = t;
+  }
+}
 
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
@@ -299,6 +308,200 @@ __global__ void __launch_bounds__(IT_THREADS, 1) itc_scan_kernel(const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------- pass 1 (v2)
+// Row statistics with the 128 x 256 query tile held in TENSOR MEMORY as the A operand (128 lanes x 256 fp32 columns):
+// all 224 KB of shared memory become a 7-deep ring of 32-key tiles.  With the queries in shared memory only two key
+// tiles fit, and each SM had < 64 KB in flight against ~1.5 us of HBM latency (72 us per scan, 16 % of HBM peak).
+// A tcgen05.mma reads its whole A slice (128 rows x 32 B = 4 KB) whatever N is: at N = 32 the issue rate (~63 cycles
+// per MMA measured, TMEM A-read bound) not the math (16 cycles) set the pace.  Pass 1 therefore multiplies against
+// 64-key tiles (two 32-key TMA tiles side by side), 3 stages of 64 KB.
+constexpr int IT1_STAGES = 3;
+constexpr int IT1_TK = 2 * IT_TK;                 // 64 keys per MMA tile
+constexpr int IT1_K_BYTES = 2 * IT_K_BYTES;       // 64 KB per stage
+constexpr int IT1_KCH_BYTES = 2 * IT_KCH_BYTES;   // one 32-float chunk of a 64-key tile
+constexpr int IT1_SMEM = 1024 + IT1_STAGES * IT1_K_BYTES + 256;
+constexpr uint32_t IT1_QCOL = 128;  // TMEM columns: S[0], S[1] at 0 / 64, the query tile at 128..383
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc], tf32
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(IT_THREADS, 1) itc_stats_kernel(const __grid_constant__ ItcMaps maps, const ItcArgs a,
+                                                                  const float* __restrict__ qm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sK = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sK + IT1_STAGES * IT1_K_BYTES);
+  uint64_t* k_full = bars;                       // [7]
+  uint64_t* k_empty = bars + IT1_STAGES;         // [7]
+  uint64_t* s_full = bars + 2 * IT1_STAGES;      // [2]
+  uint64_t* s_empty = s_full + 2;                // [2]
+  uint64_t* q_ready = s_empty + 2;               // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) it_mark(a, 0);
+  const int split = blockIdx.x, mt = blockIdx.y, ks = blockIdx.z;
+  const int t0 = split * a.tiles_per_split, t1 = min(a.ntiles, t0 + a.tiles_per_split);
+  const int nt32 = t1 - t0;            // 32-key tiles of this split
+  const int nt = (nt32 + 1) / 2;       // 64-key MMA tiles
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.h);
+    tma_prefetch_desc(ks ? &maps.k1 : &maps.k0);
+    for (int s = 0; s < IT1_STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
+    mbar_init(q_ready, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nt > 0) {
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer: 7-deep ring of key tiles =====================
+      for (int i = 0; i < nt; ++i) {
+        const int st = i % IT1_STAGES;
+        const int halves = min(2, nt32 - 2 * i);
+        mbar_wait(&k_empty[st], ((i / IT1_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], halves * IT_K_BYTES);
+        for (int hh = 0; hh < halves; ++hh) {          // each half is an independent 32-key tile (head keys or queue keys)
+          const int t = t0 + 2 * i + hh;
+          const bool head = t < a.nh;
+          const int row = head ? ks * a.rows + 3 * a.B + t * IT_TK : (t - a.nh) * IT_TK;
+          const CUtensorMap* m = head ? &maps.h : (ks ? &maps.k1 : &maps.k0);
+#pragma unroll
+          for (int c = 0; c < IT_KC; ++c)
+            tma_load_2d(sK + st * IT1_K_BYTES + c * IT1_KCH_BYTES + hh * IT_KCH_BYTES, m, &k_full[st], c * 32, row);
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===================== MMA issuer: S = Q(tmem) . K^T =====================
+      constexpr uint32_t idesc_s = umma_idesc_tf32(IT_TM, IT1_TK, 0);
+      const uint32_t aK = smem_u32(sK);
+      it_mark(a, 1);
+      mbar_wait(q_ready, 0);
+      tc_fence_after();
+      it_mark(a, 2);
+      for (int i = 0; i < nt; ++i) {
+        const int st = i % IT1_STAGES, ab = i & 1;
+        if (i < 12) it_mark(a, 8 + 3 * i);
+        mbar_wait(&k_full[st], (i / IT1_STAGES) & 1);
+        if (i < 12) it_mark(a, 9 + 3 * i);
+        mbar_wait(&s_empty[ab], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (i < 12) it_mark(a, 10 + 3 * i);
+#pragma unroll
+        for (int c = 0; c < IT_KC; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 8 tf32 of K per MMA = 8 TMEM columns of the query tile
+            tc_mma_tf32_ts(tmem_base + ab * IT1_TK, tmem_base + IT1_QCOL + c * 32 + k * 8,
+                           umma_smem_desc(aK + st * IT1_K_BYTES + c * IT1_KCH_BYTES + k * 32, 16, 1024), idesc_s, (c | k) != 0);
+        tc_commit(&s_full[ab]);
+        tc_commit(&k_empty[st]);
+      }
+      it_mark(a, 3);
+    } else if (warp >= 2) {
+      // ===================== softmax-statistics warps: thread = one query row =====================
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      const int gr = mt * IT_TM + r;
+      const bool row_ok = gr < a.rows;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      // the thread's query row (TF32-rounded by itc_normalize_kernel) goes into its TMEM lane
+      {
+        const float4* src = reinterpret_cast<const float4*>(qm + ((size_t)ks * a.rows + (row_ok ? gr : 0)) * E_);
+#pragma unroll 1
+        for (int c = 0; c < E_ / 32; ++c) {
+          uint32_t v[32];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 f = row_ok ? __ldg(src + c * 8 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * u] = __float_as_uint(f.x); v[4 * u + 1] = __float_as_uint(f.y);
+            v[4 * u + 2] = __float_as_uint(f.z); v[4 * u + 3] = __float_as_uint(f.w);
+          }
+          tmem_st32(lane_addr + IT1_QCOL + c * 32, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(q_ready);
+        if (warp == 2 && lane == 0) it_mark(a, 4);
+      }
+      const float c2 = LOG2E / __ldg(a.temp);               // logits in log2 units
+      float mx = -INFINITY, sum = 0.f;
+      for (int i = 0; i < nt; ++i) {
+        const int ab = i & 1;
+        mbar_wait(&s_full[ab], (i >> 1) & 1);
+        tc_fence_after();
+        uint32_t sr[2][32];
+        tmem_ld32(lane_addr + ab * IT1_TK, sr[0]);
+        tmem_ld32(lane_addr + ab * IT1_TK + 32, sr[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[ab]);
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int t = t0 + 2 * i + hh;
+          const int nvalid = (t >= t1) ? 0 : (t < a.nh) ? min(IT_TK, a.B - t * IT_TK) : min(IT_TK, a.Q - (t - a.nh) * IT_TK);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = (j < nvalid) ? __uint_as_float(sr[hh][j]) * c2 : -INFINITY;
+            sr[hh][j] = __float_as_uint(x);
+            tmax = fmaxf(tmax, x);
+          }
+        }
+        if (tmax > mx) { sum *= fast_exp2(mx - tmax); mx = tmax; }
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s4[j & 3] += fast_exp2(__uint_as_float(sr[hh][j]) - mx);
+        sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      }
+      if (warp == 2 && lane == 0) it_mark(a, 5);
+      if (row_ok) {
+        float* p = a.part + ((((size_t)ks * a.splits + split) * gridDim.y * IT_TM) + gr) * 2;
+        p[0] = mx;
+        p[1] = sum;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+  if (threadIdx.x == 0) it_mark(a, 6);
+}
+
 // F.normalize(z, dim=-1) for the four feature matrices (eps 1e-12); one warp per row.  Writes the exact features
 // (outputs + chain rule) and the two TF32-rounded query matrices Qm[ks] = [student 2B | teacher 2B]:
 //   ks 0 (keys = [m_text | text queue]): f_prop, f_text, m_prop, m_text
@@ -475,6 +678,12 @@ static int itc_map(CUtensorMap* m, const float* ptr, uint64_t rows, uint32_t box
 }  // namespace spmm
 using namespace spmm;
 
+static unsigned long long* g_itc_trace = nullptr;
+extern "C" int spmm_itc_debug_trace(void* buf) {   /* 64 x u64 stamps of CTA (0,0,0) of the pass-1 kernel; NULL = off */
+  g_itc_trace = reinterpret_cast<unsigned long long*>(buf);
+  return 0;
+}
+
 extern "C" int64_t spmm_itc_workspace_bytes(int B, int E, int Q) {
   if (E != E_ || B < 1 || Q < 0) return -1;
   const ItcPlan p = itc_plan(B, Q);
@@ -533,11 +742,14 @@ extern "C" int spmm_itc_fwd_bwd(const float* z_prop, const float* z_text, const 
   a.B = B; a.Q = Q; a.rows = 4 * B;
   a.nh = pl.nh; a.ntiles = pl.ntiles; a.tiles_per_split = pl.tps; a.splits = pl.splits;
   a.temp = temp; a.part = part; a.lse = lse; a.oacc = oacc;
+  a.trace = g_itc_trace;
 
   static bool configured = false;
   if (!configured) {
     cudaError_t e1 = cudaFuncSetAttribute(itc_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, IT_SMEM);
     cudaError_t e2 = cudaFuncSetAttribute(itc_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IT_SMEM);
+    cudaError_t e3 = cudaFuncSetAttribute(itc_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IT1_SMEM);
+    if (e3 != cudaSuccess) return (int)e3;
     if (e1 != cudaSuccess) return (int)e1;
     if (e2 != cudaSuccess) return (int)e2;
     configured = true;
@@ -550,7 +762,9 @@ extern "C" int spmm_itc_fwd_bwd(const float* z_prop, const float* z_text, const 
   itc_inbatch_kernel<<<dim3(B, 2), 128, 0, st>>>(feats, temp, sim_i2t, sim_t2i, B);
   SPMM_CHECK_LAUNCH();
   dim3 grid(pl.splits, pl.mtiles, 2);
-  itc_scan_kernel<1><<<grid, IT_THREADS, IT_SMEM, st>>>(maps, a);
+  static const bool pass1_smem = getenv("SPMM_ITC_PASS1_SMEM") != nullptr;   // A/B: queries in shared memory (2 key stages)
+  if (pass1_smem) itc_scan_kernel<1><<<grid, IT_THREADS, IT_SMEM, st>>>(maps, a);
+  else itc_stats_kernel<<<grid, IT_THREADS, IT1_SMEM, st>>>(maps, a, qm);
   SPMM_CHECK_LAUNCH();
   const int total = 2 * pl.rows_pad;
   itc_combine_kernel<<<(total + 255) / 256, 256, 0, st>>>(part, lse, pl.splits, pl.rows_pad, 4 * B, total);
