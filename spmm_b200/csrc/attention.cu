@@ -336,6 +336,10 @@ int attn_fwd_tc_launch(const void* q, int ldq, const void* k, int ldk, const voi
                        int batch, int heads, int Tq, int Tk, const int* kv_len, int causal, int kv_bstride, float scale,
                        uint32_t thresh16, float inv_keep, unsigned long long seed, cudaStream_t st);   // attention_tc.cu
 void attn_set_trace(void* p);
+int attn_bwd_tc_launch(const void* d_o, int lddo, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                       const float* lse, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int batch, int heads,
+                       int Tq, int Tk, const int* kv_len, int causal, float scale, uint32_t thresh16, float inv_keep,
+                       unsigned long long seed, cudaStream_t st);   // attention_tc.cu
 
 static inline void attn_drop(float p, uint32_t& th, float& ik) {
   th = p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u;
@@ -393,6 +397,11 @@ extern "C" int spmm_attn_bwd(const void* d_o, int lddo, const void* q, int ldq, 
   SPMM_ARG((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)d_o) & 15) == 0);
   uint32_t th; float ik;
   attn_drop(dropout_p, th, ik);
+  cudaStream_t st0 = (cudaStream_t)stream;
+  if (!getenv("SPMM_ATTN_LEGACY") && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 && lddo % 8 == 0 &&
+      (((uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0)
+    return attn_bwd_tc_launch(d_o, lddo, q, ldq, k, ldk, v, ldv, lse, dq, lddq, dk, lddk, dv, lddv, batch, heads, Tq, Tk, kv_len,
+                              causal, scale, th, ik, seed, st0);
   const int KT = Tk <= 64 ? 64 : 128;
   // phase 2 assigns 16 keys per warp, phase 1 16 queries per warp: the CTA needs max(Tq, Tk)/16 warps
   const int QT = (Tq <= 64 && Tk <= 64) ? 64 : 128;

@@ -433,3 +433,352 @@ int attn_fwd_tc_launch(const void* q, int ldq, const void* k, int ldk, const voi
 }
 
 }  // namespace spmm
+
+// =====================================================================================================================
+// Backward on the same tile geometry (autograd of xbert.py:305-354).  Per 128 x 128 tile (one head, or a pair of heads
+// on the diagonal blocks) five UMMA chains, all operands in the layouts TMA / the softmax threads already produce:
+//   S  = Q K^T          A = Q  (K-major)    B = K  (K-major)          recompute; P = exp(S scale - LSE)
+//   dP = dO V^T         A = dO (K-major)    B = V  (K-major)
+//   dV = Pd^T dO        A = Pd (MN-major: [query][key] tile read with M = keys)    B = dO (MN-major)
+//   dK = dS^T Q         A = dS (MN-major)   B = Q  (MN-major)         dS already carries `scale`
+//   dQ = dS K           A = dS (K-major)    B = K  (MN-major)
+// with Pd = P o dropout-mask / keep, D_i = sum_j Pd_ij dP_ij, dS = P o (dP o mask / keep - D) * scale.
+// 576 threads: TMA producer (2-stage Q/K/V/dO ring), MMA issuer, 16 softmax warps = 4 threads per tile row (each
+// owns 32 key columns).  dQ / dK / dV leave through 3-D bulk tensor stores (rows beyond the sequence are clipped).
+namespace spmm {
+
+constexpr int AB_STAGE_BYTES = 4 * AT_TILE_BYTES;            // Q, K, V, dO
+constexpr int AB_STAGES = 2;
+constexpr int AB_PDS_BYTES = 4 * AT_TILE_BYTES;              // Pd (2 chunks) + dS (2 chunks); reused as dQ/dK/dV staging
+constexpr int AB_XCH_BYTES = 128 * 4 * 4;
+constexpr int AB_SMEM = 1024 + AB_STAGES * AB_STAGE_BYTES + AB_PDS_BYTES + AB_XCH_BYTES + 512;
+constexpr uint32_t AB_S = 0, AB_DP = 128, AB_DK = 256, AB_DV = 320, AB_DQ = 384;   // TMEM columns
+
+struct AttnBwdMaps { CUtensorMap q, k, v, dout, dq, dk, dv; };
+
+struct AttnBwdArgs {
+  const float* lse;
+  int batch, heads, Tq, Tk;
+  const int* kv_len;
+  int causal;
+  float scale;
+  unsigned long long seed;
+  uint32_t thresh16;
+  float inv_keep;
+  const unsigned long long* salt;
+  int pair, hp, num_tiles;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sPd = smem + AB_STAGES * AB_STAGE_BYTES;          // [2 chunks][128 rows][128 B]
+  uint8_t* sdS = sPd + 2 * AT_TILE_BYTES;
+  float* xch = reinterpret_cast<float*>(sPd + AB_PDS_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPd + AB_PDS_BYTES + AB_XCH_BYTES);
+  uint64_t* full = bars;            // [2]
+  uint64_t* empty = bars + 2;       // [2]
+  uint64_t* sdp_full = bars + 4;    // S and dP accumulators ready
+  uint64_t* sdp_free = bars + 5;    // softmax threads have read S and dP (16 warps)
+  uint64_t* pds_full = bars + 6;    // Pd and dS operand tiles written (16 warps)
+  uint64_t* out_full = bars + 7;    // dQ, dK, dV accumulators ready
+  uint64_t* acc_free = bars + 8;    // dQ, dK, dV accumulators read (16 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.v); tma_prefetch_desc(&maps.dout);
+    tma_prefetch_desc(&maps.dq); tma_prefetch_desc(&maps.dk); tma_prefetch_desc(&maps.dv);
+    for (int s = 0; s < AB_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(sdp_full, 1); mbar_init(sdp_free, 16); mbar_init(pds_full, 16); mbar_init(out_full, 1); mbar_init(acc_free, 16);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  // forward-compatible tile decoding (same pairing as attn_fwd_tc_kernel); K/V rows are batch-major (no broadcast)
+  auto decode = [&](int tile, int& b, int& h0, int& h1, int& qrow0, int& qrow1, int& krow0, int& krow1) {
+    if (a.pair) {
+      b = tile / a.hp; h0 = 2 * (tile % a.hp); h1 = min(h0 + 1, a.heads - 1);
+      qrow0 = qrow1 = b * a.Tq; krow0 = krow1 = b * a.Tk;
+    } else {
+      b = tile / a.heads; h0 = h1 = tile % a.heads;
+      qrow0 = b * a.Tq; qrow1 = qrow0 + 64; krow0 = b * a.Tk; krow1 = krow0 + 64;
+    }
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int n = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++n) {
+      const int st = n % AB_STAGES;
+      mbar_wait(&empty[st], ((n / AB_STAGES) & 1) ^ 1);
+      int b, h0, h1, q0, q1, k0, k1;
+      decode(tile, b, h0, h1, q0, q1, k0, k1);
+      uint8_t* sq = smem + st * AB_STAGE_BYTES;
+      uint8_t* sk = sq + AT_TILE_BYTES;
+      uint8_t* sv = sk + AT_TILE_BYTES;
+      uint8_t* sdo = sv + AT_TILE_BYTES;
+      mbar_expect_tx(&full[st], AB_STAGE_BYTES);
+      tma_load_2d(sq, &maps.q, &full[st], h0 * 64, q0);
+      tma_load_2d(sq + AT_TILE_BYTES / 2, &maps.q, &full[st], h1 * 64, q1);
+      tma_load_2d(sk, &maps.k, &full[st], h0 * 64, k0);
+      tma_load_2d(sk + AT_TILE_BYTES / 2, &maps.k, &full[st], h1 * 64, k1);
+      tma_load_2d(sv, &maps.v, &full[st], h0 * 64, k0);
+      tma_load_2d(sv + AT_TILE_BYTES / 2, &maps.v, &full[st], h1 * 64, k1);
+      tma_load_2d(sdo, &maps.dout, &full[st], h0 * 64, q0);
+      tma_load_2d(sdo + AT_TILE_BYTES / 2, &maps.dout, &full[st], h1 * 64, q1);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t id_kk = umma_idesc_bf16(128, 128, 0, 0);   // S, dP: both operands K-major (head_dim contiguous)
+    const uint32_t id_mm = umma_idesc_bf16(128, 64, 1, 1);    // dV, dK: A = [query][key] tile read MN-major, B MN-major
+    const uint32_t id_km = umma_idesc_bf16(128, 64, 0, 1);    // dQ: A = dS K-major, B = K MN-major
+    const uint32_t aPd = smem_u32(sPd), adS = smem_u32(sdS);
+    int n = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++n) {
+      const int st = n % AB_STAGES;
+      const uint32_t ph = n & 1;
+      const uint32_t sq = smem_u32(smem + st * AB_STAGE_BYTES), sk = sq + AT_TILE_BYTES, sv = sk + AT_TILE_BYTES,
+                     sdo = sv + AT_TILE_BYTES;
+      mbar_wait(&full[st], (n / AB_STAGES) & 1);
+      mbar_wait(sdp_free, ph ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        tc_mma_bf16(tmem_base + AB_S, umma_smem_desc(sq + k * 32, 16, 1024), umma_smem_desc(sk + k * 32, 16, 1024), id_kk, k != 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        tc_mma_bf16(tmem_base + AB_DP, umma_smem_desc(sdo + k * 32, 16, 1024), umma_smem_desc(sv + k * 32, 16, 1024), id_kk, k != 0);
+      tc_commit(sdp_full);
+      mbar_wait(pds_full, ph);
+      mbar_wait(acc_free, ph ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)   // 16 queries per MMA
+        tc_mma_bf16(tmem_base + AB_DV, umma_smem_desc(aPd + k * 2048, 2 * 8192, 1024), umma_smem_desc(sdo + k * 2048, 8192, 1024), id_mm, k != 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        tc_mma_bf16(tmem_base + AB_DK, umma_smem_desc(adS + k * 2048, 2 * 8192, 1024), umma_smem_desc(sq + k * 2048, 8192, 1024), id_mm, k != 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)   // 16 keys per MMA
+        tc_mma_bf16(tmem_base + AB_DQ, umma_smem_desc(adS + (k >> 2) * AT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                    umma_smem_desc(sk + k * 2048, 8192, 1024), id_km, k != 0);
+      tc_commit(out_full);
+      tc_commit(&empty[st]);
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax-backward threads: 4 per tile row, 32 key columns each =====================
+    const int sw = warp - 2;
+    const int part = sw >> 2, q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t drop_key = a.thresh16 ? fold_seed(salted(a.seed, a.salt)) : 0u;
+    const float c2 = a.scale * AT_LOG2E;
+    const int slot = a.pair ? (r >> 6) : 0;
+    const int i = a.pair ? (r & 63) : r;
+    const int col0 = a.pair ? 64 * slot : 0;
+    const int ncol = a.pair ? 64 : 128;
+    const int cc = 32 * part - col0;                       // first key (within the head) of this thread's chunk
+    const bool mine = cc >= 0 && cc < ncol;                // warp-uniform
+    const bool elected = (sw == 0 && lane == 0);
+    uint8_t* pd_row = sPd + (part >> 1) * AT_TILE_BYTES + r * 128;
+    uint8_t* ds_row = sdS + (part >> 1) * AT_TILE_BYTES + r * 128;
+    const int u0 = (part & 1) * 4;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++n) {
+      int b, h0, h1, q0r, q1r, k0r, k1r;
+      decode(tile, b, h0, h1, q0r, q1r, k0r, k1r);
+      const int h = a.pair ? h0 + slot : h0;
+      const bool head_ok = h < a.heads;
+      const bool valid = head_ok && (i < a.Tq);
+      const int klen = a.kv_len ? min(__ldg(a.kv_len + b), a.Tk) : a.Tk;
+      const int jmax = a.causal ? min(klen, i + 1) : klen;
+      const int bh = b * a.heads + h;
+      const float lse2 = valid ? __ldg(a.lse + (size_t)bh * a.Tq + i) * AT_LOG2E : 0.f;
+      const uint32_t ph = n & 1;
+      mbar_wait(sdp_full, ph);
+      tc_fence_after();
+      float p[32], dpk[32];
+      float dpart = 0.f;
+      uint32_t kmask = 0xFFFFFFFFu;                        // dropout keep bits of this thread's 32 keys
+      const bool blk = mine && cc < klen;                  // warp-uniform
+      if (blk) {
+        uint32_t sr[32], dr[32];
+        tmem_ld32(lane_addr + AB_S + 32 * part, sr);
+        tmem_ld32(lane_addr + AB_DP + 32 * part, dr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          p[j] = (valid && cc + j < jmax) ? at_exp2(__uint_as_float(sr[j]) * c2 - lse2) : 0.f;
+          dpk[j] = __uint_as_float(dr[j]);
+        }
+        if (a.thresh16) {
+#pragma unroll
+          kmask = 0u;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const uint32_t hb = at_drop_bits(drop_key, bh, i, cc + j);
+            const bool k0 = (hb & 0xFFFFu) >= a.thresh16, k1 = (hb >> 16) >= a.thresh16;
+            kmask |= (k0 ? 1u : 0u) << j;
+            kmask |= (k1 ? 1u : 0u) << (j + 1);
+            dpk[j] = k0 ? dpk[j] * a.inv_keep : 0.f;
+            dpk[j + 1] = k1 ? dpk[j + 1] * a.inv_keep : 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dpart += p[j] * dpk[j];     // = Pd_ij dP_ij (keep factor already in dpk)
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { p[j] = 0.f; dpk[j] = 0.f; }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_free);
+      xch[r * 4 + part] = dpart;
+      // the Pd / dS tiles double as the output staging of the previous tile: wait until its bulk stores have read them
+      if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      bar_sync_at(1, 512);
+      const float D = (xch[r * 4] + xch[r * 4 + 1]) + (xch[r * 4 + 2] + xch[r * 4 + 3]);
+      // Pd = p * keep (keep = mask / keep_prob, bits kept in kmask)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t wp[4], wd[4];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          const int j = 8 * u + 2 * e2;
+          const float kf = a.thresh16 ? a.inv_keep : 1.f;
+          const float k0f = ((kmask >> j) & 1u) ? kf : 0.f, k1f = ((kmask >> (j + 1)) & 1u) ? kf : 0.f;
+          wp[e2] = pack_bf16x2(p[j] * k0f, p[j + 1] * k1f);
+          wd[e2] = pack_bf16x2(p[j] * (dpk[j] - D) * a.scale, p[j + 1] * (dpk[j + 1] - D) * a.scale);
+        }
+        *reinterpret_cast<uint4*>(pd_row + (((u0 + u) ^ (r & 7)) << 4)) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+        *reinterpret_cast<uint4*>(ds_row + (((u0 + u) ^ (r & 7)) << 4)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      // ---- outputs: part 0/1 -> dQ and dV column halves, part 2/3 -> dK column halves (lanes = query / key rows)
+      mbar_wait(out_full, ph);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      if (part < 2) {
+        tmem_ld32(lane_addr + AB_DQ + 32 * part, o0);
+        tmem_ld32(lane_addr + AB_DV + 32 * part, o1);
+      } else {
+        tmem_ld32(lane_addr + AB_DK + 32 * (part - 2), o0);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);
+      // staging tiles ([128 rows][128 B], swizzled) in the Pd / dS region (the MMAs that read it are complete): dQ | dK | dV
+      {
+        uint8_t* t0 = sPd + (part < 2 ? 0 : AT_TILE_BYTES) + r * 128;
+        const int uu = (part & 1) * 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o0[8 * u]), __uint_as_float(o0[8 * u + 1]));
+          w.y = pack_bf16x2(__uint_as_float(o0[8 * u + 2]), __uint_as_float(o0[8 * u + 3]));
+          w.z = pack_bf16x2(__uint_as_float(o0[8 * u + 4]), __uint_as_float(o0[8 * u + 5]));
+          w.w = pack_bf16x2(__uint_as_float(o0[8 * u + 6]), __uint_as_float(o0[8 * u + 7]));
+          *reinterpret_cast<uint4*>(t0 + (((uu + u) ^ (r & 7)) << 4)) = w;
+        }
+        if (part < 2) {
+          uint8_t* t1 = sPd + 2 * AT_TILE_BYTES + r * 128;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o1[8 * u]), __uint_as_float(o1[8 * u + 1]));
+            w.y = pack_bf16x2(__uint_as_float(o1[8 * u + 2]), __uint_as_float(o1[8 * u + 3]));
+            w.z = pack_bf16x2(__uint_as_float(o1[8 * u + 4]), __uint_as_float(o1[8 * u + 5]));
+            w.w = pack_bf16x2(__uint_as_float(o1[8 * u + 6]), __uint_as_float(o1[8 * u + 7]));
+            *reinterpret_cast<uint4*>(t1 + (((uu + u) ^ (r & 7)) << 4)) = w;
+          }
+        }
+      }
+      fence_proxy_async();
+      bar_sync_at(1, 512);
+      if (elected) {
+        uint8_t* sdq = sPd;
+        uint8_t* sdk = sPd + AT_TILE_BYTES;
+        uint8_t* sdv = sPd + 2 * AT_TILE_BYTES;
+        if (a.pair) {
+          at_tma_store_3d(&maps.dq, sdq, h0 * 64, 0, b);
+          at_tma_store_3d(&maps.dk, sdk, h0 * 64, 0, b);
+          at_tma_store_3d(&maps.dv, sdv, h0 * 64, 0, b);
+          if (h0 + 1 < a.heads) {
+            at_tma_store_3d(&maps.dq, sdq + AT_TILE_BYTES / 2, (h0 + 1) * 64, 0, b);
+            at_tma_store_3d(&maps.dk, sdk + AT_TILE_BYTES / 2, (h0 + 1) * 64, 0, b);
+            at_tma_store_3d(&maps.dv, sdv + AT_TILE_BYTES / 2, (h0 + 1) * 64, 0, b);
+          }
+        } else {
+          at_tma_store_3d(&maps.dq, sdq, h0 * 64, 0, b);
+          at_tma_store_3d(&maps.dk, sdk, h0 * 64, 0, b);
+          at_tma_store_3d(&maps.dv, sdv, h0 * 64, 0, b);
+          if (a.Tq > 64) at_tma_store_3d(&maps.dq, sdq + AT_TILE_BYTES / 2, h0 * 64, 64, b);
+          if (a.Tk > 64) {
+            at_tma_store_3d(&maps.dk, sdk + AT_TILE_BYTES / 2, h0 * 64, 64, b);
+            at_tma_store_3d(&maps.dv, sdv + AT_TILE_BYTES / 2, h0 * 64, 64, b);
+          }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int attn_bwd_tc_launch(const void* d_o, int lddo, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                       const float* lse, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int batch, int heads,
+                       int Tq, int Tk, const int* kv_len, int causal, float scale, uint32_t thresh16, float inv_keep,
+                       unsigned long long seed, cudaStream_t st) {
+  AttnBwdMaps maps;
+  int rc = attn_make_map(&maps.q, q, (uint64_t)heads * 64, (uint64_t)batch * Tq, ldq);
+  if (rc) return rc;
+  rc = attn_make_map(&maps.dout, d_o, (uint64_t)heads * 64, (uint64_t)batch * Tq, lddo);
+  if (rc) return rc;
+  rc = attn_make_map(&maps.k, k, (uint64_t)heads * 64, (uint64_t)batch * Tk, ldk);
+  if (rc) return rc;
+  rc = attn_make_map(&maps.v, v, (uint64_t)heads * 64, (uint64_t)batch * Tk, ldv);
+  if (rc) return rc;
+  rc = attn_make_map3d(&maps.dq, dq, (uint64_t)heads * 64, Tq, batch, lddq);
+  if (rc) return rc;
+  rc = attn_make_map3d(&maps.dk, dk, (uint64_t)heads * 64, Tk, batch, lddk);
+  if (rc) return rc;
+  rc = attn_make_map3d(&maps.dv, dv, (uint64_t)heads * 64, Tk, batch, lddv);
+  if (rc) return rc;
+  AttnBwdArgs a{};
+  a.lse = lse; a.batch = batch; a.heads = heads; a.Tq = Tq; a.Tk = Tk; a.kv_len = kv_len; a.causal = causal; a.scale = scale;
+  a.seed = seed; a.thresh16 = thresh16; a.inv_keep = inv_keep; a.salt = spmm_g_rng_salt;
+  a.pair = (Tq <= 64 && Tk <= 64) ? 1 : 0;
+  a.hp = (heads + 1) / 2;
+  a.num_tiles = a.pair ? batch * a.hp : batch * heads;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int ctas = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
+  cudaError_t le = launch_pdl(attn_bwd_tc_kernel, dim3(ctas), dim3(AT_THREADS), AB_SMEM, st, maps, a);
+  if (le != cudaSuccess) return (int)le;
+  return 0;
+}
+
+}  // namespace spmm
