@@ -302,6 +302,40 @@ def test_attention_fwd_bwd(B, h, Tq, Tk, causal, ragged):
     assert rel_err(dv, flat(vf.grad, Tk)) < 2e-2, ("dv", rel_err(dv, flat(vf.grad, Tk)))
 
 
+@pytest.mark.parametrize("B,h,Tq,Tk,causal", [(3, 12, 64, 64, False), (2, 4, 54, 99, False), (2, 12, 99, 99, True)])
+def test_attention_dropout_forward_backward_share_the_mask(B, h, Tq, Tk, causal):
+    """With attention dropout the forward and backward kernels regenerate the same keep mask from (seed, head, i, j).
+    For a fixed mask O = Pd V is linear in V, so <dO, O> == <dV, V> (adjoint identity) holds only if both directions
+    used the same Pd; the keep rate is checked through O's deviation from the no-dropout output."""
+    H = h * 64
+    q = rnd(B * Tq, H, dtype=BF, seed=1)
+    kv = rnd(B * Tk, 2 * H, dtype=BF, seed=2)
+    k, v = kv[:, :H], kv[:, H:]
+    o, lse = torch.empty(B * Tq, H, device=DEV, dtype=BF), torch.empty(B * h * Tq, device=DEV)
+    K.attn_fwd(q, k, v, o, lse, B, h, Tq, Tk, None, causal, 0.125, 0.1, 77)
+    o_again = torch.empty_like(o)
+    K.attn_fwd(q, k, v, o_again, None, B, h, Tq, Tk, None, causal, 0.125, 0.1, 77)
+    assert torch.equal(o, o_again)                      # mask is a pure function of the seed
+    o_other = torch.empty_like(o)
+    K.attn_fwd(q, k, v, o_other, None, B, h, Tq, Tk, None, causal, 0.125, 0.1, 78)
+    assert not torch.equal(o, o_other)
+    do = rnd(B * Tq, H, dtype=BF, seed=4)
+    dq = torch.zeros(B * Tq, H, device=DEV, dtype=BF)
+    dkv = torch.zeros(B * Tk, 2 * H, device=DEV, dtype=BF)
+    K.attn_bwd(do, q, k, v, o, lse, dq, dkv[:, :H], dkv[:, H:], B, h, Tq, Tk, None, causal, 0.125, 0.1, 77)
+    lhs = float((do.float() * o.float()).sum())
+    rhs = float((dkv[:, H:].float() * v.float()).sum())
+    scale = float((do.float() * o.float()).pow(2).sum().sqrt())     # natural spread of the (random-sign) sum
+    print("adjoint: <dO,O> %.4f  <dV,V> %.4f  spread %.3f" % (lhs, rhs, scale))
+    assert abs(lhs - rhs) < 3e-2 * scale, (lhs, rhs, scale)
+    # a different backward seed breaks the identity (the check is not vacuous)
+    dkv2 = torch.zeros_like(dkv)
+    K.attn_bwd(do, q, k, v, o, lse, dq, dkv2[:, :H], dkv2[:, H:], B, h, Tq, Tk, None, causal, 0.125, 0.1, 78)
+    rhs2 = float((dkv2[:, H:].float() * v.float()).sum())
+    print("other seed: <dV',V> %.4f  rel-L2(dV' - dV) %.3f" % (rhs2, rel_err(dkv2[:, H:], dkv[:, H:])))
+    assert rel_err(dkv2[:, H:], dkv[:, H:]) > 0.1       # ~18 % of the (i, j) pairs change their keep bit
+
+
 def test_attention_kv_broadcast():
     B, h, Tq, Tk, H = 4, 12, 9, 54, 768
     q, kv = rnd(B * Tq, H, dtype=BF, seed=1), rnd(Tk, 2 * H, dtype=BF, seed=2)
