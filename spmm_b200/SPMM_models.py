@@ -285,6 +285,69 @@ class SPMM(_Base):
         K.enqueue(self.prop_queue_km, self.text_queue_km, feats[0], feats[1], self.queue_ptr, skip_flag)
 
     # ------------------------------------------------------------------ optimiser / Lightning-style hooks
+    # ------------------------------------------------------------------ Lightning-shaped hooks (reference :345-386)
+    # pytorch_lightning is not a dependency: `trainer.fit` (spmm_b200/trainer.py) plays the Trainer and sets the handful of
+    # attributes these hooks read (optimizers / lr_schedulers / current_epoch / global_rank / log).
+    current_epoch = 0
+    global_rank = 0
+
+    def attach(self, optimizer, scheduler, global_rank=0, log=None):
+        self._opt, self._sched, self.global_rank = optimizer, scheduler, global_rank
+        self._log = log
+        self._stepper = None
+        return self
+
+    def optimizers(self):
+        return self._opt
+
+    def lr_schedulers(self):
+        return self._sched
+
+    def log(self, name, value, prog_bar=False):
+        if getattr(self, "_log", None) is not None:
+            self._log(name, value)
+
+    def lr_scheduler_step(self, scheduler, optimizer_idx, metric):       # reference :345-346 (manual optimisation)
+        pass
+
+    def training_step(self, train_batch, batch_idx):
+        """Reference SPMM_models.py:348-380: tokenise, alpha ramp (epoch 0), forward/backward/clip/AdamW (one fused
+        `trainer.train_step`, or its CUDA graph), cosine schedule stepping with the reference's warm-up cadence.
+        Returns the four losses as ONE device tensor (no host sync; the reference's `loss != 0` NaN check is a device
+        flag that skips the optimiser step)."""
+        from . import trainer
+        optimizer, scheduler = self.optimizers(), self.lr_schedulers()
+        prop, text = train_batch
+        dev = self.arena().device
+        if isinstance(text, (list, tuple)) and len(text) > 0 and isinstance(text[0], str):      # SMILES strings
+            text_input = self.tokenizer(text, padding='longest', truncation=True, max_length=100, return_tensors="pt")
+            ids, mask = text_input.input_ids[:, 1:], text_input.attention_mask[:, 1:]
+        else:                                      # pre-tokenised (ids, mask) pair
+            ids, mask = text
+        alpha = self.config['alpha'] if self.current_epoch > 0 else \
+            self.config['alpha'] * min(1., batch_idx / max(self.loader_len, 1))
+        prop, ids, mask = prop.to(dev, non_blocking=True), ids.to(dev, non_blocking=True), mask.to(dev, non_blocking=True)
+        losses = torch.stack([l.detach() for l in trainer.train_step(self, optimizer, prop, ids, mask, alpha)])
+        if self.global_rank == 0:
+            self.log('lr', optimizer.param_groups[0]["lr"], prog_bar=True)
+            for name, l in zip(('loss_mlm', 'loss_mpm', 'loss_ita', 'loss_itm'), losses):
+                self.log(name, l, prog_bar=True)
+        step_size = 100
+        warmup_iterations = self.warmup_steps * step_size
+        if self.current_epoch > 0 and batch_idx == 0:
+            scheduler.step(self.current_epoch + self.warmup_steps)
+        elif self.current_epoch == 0 and batch_idx % step_size == 0 and batch_idx <= warmup_iterations:
+            scheduler.step(batch_idx // step_size)
+        self.training_step_outputs.append(losses)
+        return losses
+
+    def on_train_epoch_end(self):                  # reference :382-386
+        tmp = torch.stack(self.training_step_outputs[-1000:]).float().mean(dim=0).tolist()
+        if self.global_rank == 0:
+            print(f'\n mean loss: {tmp[0]:.4f}, {tmp[1]:.4f}, {tmp[2]:.4f}, {tmp[3]:.4f}')
+        self.training_step_outputs.clear()
+        return tmp
+
     def configure_optimizers(self):
         from .optim import FusedClipAdamW
         from .scheduler import create_scheduler

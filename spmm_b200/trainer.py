@@ -107,3 +107,20 @@ class GraphedTrainStep:
         self.opt.prepare_step()
         st["graph"].replay()
         return st["losses"]
+
+
+def fit(model, loader, max_epochs=1, log=None):
+    """What `SPMM_pretrain.py:12-37` asks of `pl.Trainer(...).fit(model, data_loader)`, without Lightning: one process
+    per GPU (torchrun), `model` already on its device.  Builds the optimiser / scheduler from `configure_optimizers`,
+    then runs the reference's hooks: training_step per batch, on_train_epoch_end per epoch."""
+    (optimizer,), (scheduler,) = model.configure_optimizers()
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    model.attach(optimizer, scheduler, global_rank=rank, log=log)
+    model.train()
+    history = []
+    for epoch in range(max_epochs):
+        model.current_epoch = epoch
+        for batch_idx, batch in enumerate(loader):
+            model.training_step(batch, batch_idx)
+        history.append(model.on_train_epoch_end())
+    return history

@@ -172,3 +172,41 @@ def test_data_parallel_plumbing_gloo_world2(tmp_path):
     assert torch.equal(r["grad"], torch.full((5,), 1.5))
     # queue divisibility rule of the reference (SPMM_models.py:279) for W in {1,2,4,8} at B=96
     assert all(36864 % (96 * w) == 0 for w in (1, 2, 4, 8))
+
+
+def test_lightning_shaped_hooks_follow_the_reference_schedule(monkeypatch):
+    """training_step / on_train_epoch_end (reference SPMM_models.py:348-386) without Lightning: alpha ramp over epoch 0,
+    scheduler stepping every 100 batches of the warm-up and once per later epoch, epoch mean of the last 1000 steps.
+    The fused device step itself is stubbed (no GPU here)."""
+    from types import SimpleNamespace
+    from spmm_b200 import synth, trainer
+    from spmm_b200.SPMM_models import SPMM
+    cfg = synth.pretrain_config(os.path.join(CFG, "config_tiny_text.json"), os.path.join(CFG, "config_tiny_property.json"), 96, 6)
+    cfg["schedular"]["warmup_epochs"] = 2
+    model = SPMM(config=cfg, loader_len=400)
+    seen = {"alpha": [], "sched": []}
+
+    def fake_step(m, opt, prop, ids, mask, alpha, **kw):
+        seen["alpha"].append(alpha)
+        n = float(len(seen["alpha"]))
+        return [torch.tensor(n), torch.tensor(2 * n), torch.tensor(3 * n), torch.tensor(4 * n)]
+    monkeypatch.setattr(trainer, "train_step", fake_step)
+    monkeypatch.setattr(SPMM, "arena", lambda self: SimpleNamespace(device=torch.device("cpu")))
+    opt = SimpleNamespace(param_groups=[{"lr": 1e-4}])
+    sched = SimpleNamespace(step=lambda e: seen["sched"].append(e))
+    model.attach(opt, sched, global_rank=0, log=None)
+    batch = (torch.zeros(6, 53), (torch.ones(6, 12, dtype=torch.long), torch.ones(6, 12, dtype=torch.long)))
+    model.current_epoch = 0
+    for i in (0, 50, 100, 200, 300, 399):
+        out = model.training_step(batch, i)
+        assert out.shape == (4,)
+    a = cfg["alpha"]
+    assert seen["alpha"] == pytest.approx([0.0, a * 50 / 400, a * 100 / 400, a * 200 / 400, a * 300 / 400, a * 399 / 400])
+    assert seen["sched"] == [0, 1, 2]                    # batches 0, 100, 200 (<= warmup_epochs * 100); 300 is past the warm-up
+    mean = model.on_train_epoch_end()
+    assert mean == pytest.approx([3.5, 7.0, 10.5, 14.0]) and model.training_step_outputs == []
+    model.current_epoch = 3
+    model.training_step(batch, 0)
+    model.training_step(batch, 100)
+    assert seen["alpha"][-2:] == [a, a]
+    assert seen["sched"] == [0, 1, 2, 3 + 2]             # one step per epoch afterwards: epoch + warmup_steps

@@ -250,3 +250,19 @@ def test_cuda_graph_step_matches_eager_step():
     upd_e = out["eager"][1] - out["graph"][1]
     assert float(upd_e.abs().max()) <= 4 * 2 * 2e-4 + 1e-6    # bounded by 2*lr per step
     assert out["eager"][2] == out["graph"][2] and out["eager"][3] == out["graph"][3]
+
+
+def test_fit_driver_runs_the_reference_hooks():
+    """trainer.fit = the reference's `pl.Trainer(...).fit` body (SPMM_pretrain.py:12-37) through training_step /
+    on_train_epoch_end with pre-tokenised batches: finite losses, queue pointer advanced by B per step, lr warm-up."""
+    from spmm_b200 import trainer
+    g = load_golden("tiny_b6")
+    model = build_model("tiny_b6", train=True)
+    model.loader_len = 3
+    batch = (g["pv"], (g["ids"], g["mask"]))
+    logged = []
+    hist = trainer.fit(model, [batch, batch, batch], max_epochs=2, log=lambda k, v: logged.append(k))
+    assert len(hist) == 2 and all(math.isfinite(x) for ep in hist for x in ep)
+    assert int(model.queue_ptr) == (6 * 6) % model.queue_size
+    assert int(model.optimizers().t_dev) == 6
+    assert "loss_ita" in logged and "lr" in logged
