@@ -7,6 +7,8 @@ Tolerances (from the reference compared with itself under
   losses |d| <= 1e-2;  per-tensor gradient rel-L2 <= 3e-2 and cosine >= 0.999 (tensors whose gradient is
   numerically zero are skipped);  global gradient rel-L2 <= 1.5e-2;  d/d temp rel <= 1e-1 (ill-conditioned: the reference vs its own bf16 autocast differs by 0.40);  EMA bit-exact.
 """
+import math
+
 import pytest
 import torch
 
