@@ -163,6 +163,16 @@ int spmm_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq,
                     float grad_scale, const float* skip_flag, const float* hyper_dev, void* stream);
 /* hyper_dev (device float[3] = lr, 1-beta1^t, sqrt(1-beta2^t)) overrides lr/step when non-NULL (graph replay). */
 
+/* ------------------------------------------------------------------ host-side WordPiece tokenizer (no CUDA)
+ * Replaces BertTokenizer(do_basic_tokenize=False) + WordpieceTokenizer(max_input_chars_per_word=250) as used by
+ * SPMM_pretrain.py:19-20 / SPMM_models.py:352 / d_smiles2pv.py:43,61: whitespace split, greedy longest-match-first
+ * ("##" continuation pieces), whole word -> unk on any miss, [cls] ... [sep], truncation to max_length,
+ * padding='longest'.  ids_out / mask_out: [n][ld] int64 host buffers (pinned for async H2D).  Returns the padded width. */
+void* spmm_wordpiece_create(const char* const* tokens, int n_tokens, int unk_id, int max_input_chars_per_word);
+void spmm_wordpiece_destroy(void* handle);
+int spmm_wordpiece_encode_batch(void* handle, const char* const* texts, int n, int max_length, int cls_id, int sep_id,
+                                int pad_id, int64_t* ids_out, int64_t* mask_out, int ld);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,9 @@ SIGNATURES = {
     "spmm_lm_loss_fwd_bwd": (i32, [vp, vp, i32, vp, i32, i32, i32, f32, vp, vp, vp, vp]),
     "spmm_itm_loss_fwd_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "spmm_mpm_loss_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "spmm_wordpiece_create": (vp, [C.POINTER(C.c_char_p), i32, i32, i32]),
+    "spmm_wordpiece_destroy": (None, [vp]),
+    "spmm_wordpiece_encode_batch": (i32, [vp, C.POINTER(C.c_char_p), i32, i32, i32, i32, i32, vp, vp, i32]),
     "spmm_ema_multi": (i32, [vp, vp, vp, vp, i64, f32, f32, vp]),
     "spmm_grad_sumsq": (i32, [vp, i64, vp, vp]),
     "spmm_adam_tick": (i32, [vp, vp, vp, f32, f32, vp, vp]),
