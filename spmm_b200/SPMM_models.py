@@ -186,6 +186,15 @@ class SPMM(_Base):
 
     # ------------------------------------------------------------------ the hot path
     def forward(self, property_original, text_input_ids, text_attention_mask, alpha=0, mpm_mask=None, neg_idx=None):
+        from .xbert import raw_outputs
+        with raw_outputs():                         # bf16 activations between the blocks of the hot path
+            return self._forward(property_original, text_input_ids, text_attention_mask, alpha, mpm_mask, neg_idx)
+
+    @property
+    def device(self):                               # LightningModule.device, read by d_smiles2pv.py:34
+        return self.arena().device if self._arena is not None else next(self.parameters()).device
+
+    def _forward(self, property_original, text_input_ids, text_attention_mask, alpha=0, mpm_mask=None, neg_idx=None):
         """Reference SPMM_models.py:79-256.  `mpm_mask` / `neg_idx=(neg_t2i, neg_i2t)` inject the random draws
         (parity tests); otherwise torch.bernoulli on the device and the counter-based sampler are used."""
         A = self.arena()

@@ -7,6 +7,7 @@ Same class names, attribute tree and state-dict keys as the reference (`BertForM
 forward pass never calls them, it launches the block kernels in spmm_b200/ops.py on views of the flat
 parameter arena (spmm_b200/arena.py).  Activations are bf16 [tokens, hidden].
 """
+import contextlib
 import json
 from types import SimpleNamespace
 
@@ -166,6 +167,25 @@ def _init_bert_weights(module, std):
             m.bias.data.zero_()
 
 
+# Activations are bf16 inside SPMM.forward (raw_outputs()); callers that reach into the sub-modules the way the d_*.py
+# scripts do (d_smiles2pv.py:15-25, d_pv2smiles_batched.py:25-27) pass fp32 embeddings and apply fp32 torch heads to the
+# result, as with the reference's fp32 modules: they get fp32 `last_hidden_state` / logits back.
+_RAW = [False]
+
+
+@contextlib.contextmanager
+def raw_outputs():
+    old, _RAW[0] = _RAW[0], True
+    try:
+        yield
+    finally:
+        _RAW[0] = old
+
+
+def _bf16(t):
+    return t if t is None or t.dtype == torch.bfloat16 else t.to(torch.bfloat16)
+
+
 class ModelOutput(SimpleNamespace):
     def __getitem__(self, i):
         return (self.last_hidden_state,)[i]
@@ -201,6 +221,7 @@ class BertModel(nn.Module):
             raise NotImplementedError("unused on the SPMM hot path")
         cfg = self.config
         bd = self._bundles()
+        inputs_embeds, encoder_embeds, encoder_hidden_states = _bf16(inputs_embeds), _bf16(encoder_embeds), _bf16(encoder_hidden_states)
         p_hid = cfg.hidden_dropout_prob if self.training else 0.0
         p_att = cfg.attention_probs_dropout_prob if self.training else 0.0
         if input_ids is not None and inputs_embeds is not None:
@@ -241,6 +262,8 @@ class BertModel(nn.Module):
                 x = ops.attn_block(x, enc, lw.cross, cross_geom, p_att, p_hid, bd.anchor)
             x = ops.ffn_block(x, lw.ffn, p_hid, bd.anchor)
         out = x.view(B, T, -1)
+        if not _RAW[0]:
+            out = out.float()
         if not return_dict:
             return (out,)
         return ModelOutput(last_hidden_state=out, pooler_output=None, past_key_values=None, hidden_states=None,
@@ -272,12 +295,13 @@ class BertForMaskedLM(nn.Module):
     def forward(self, input_ids=None, attention_mask=None, encoder_embeds=None, encoder_hidden_states=None,
                 encoder_attention_mask=None, inputs_embeds=None, return_dict=True, is_decoder=False,
                 mode='multi_modal', return_logits=False, return_hidden=False, **unused):
-        h = self.bert(input_ids, attention_mask=attention_mask, inputs_embeds=inputs_embeds,
-                      encoder_embeds=encoder_embeds, encoder_hidden_states=encoder_hidden_states,
-                      encoder_attention_mask=encoder_attention_mask, return_dict=True, is_decoder=is_decoder,
-                      mode=mode).last_hidden_state
+        with raw_outputs():
+            h = self.bert(input_ids, attention_mask=attention_mask, inputs_embeds=inputs_embeds,
+                          encoder_embeds=encoder_embeds, encoder_hidden_states=encoder_hidden_states,
+                          encoder_attention_mask=encoder_attention_mask, return_dict=True, is_decoder=is_decoder,
+                          mode=mode).last_hidden_state
         if return_hidden:
-            return h
+            return h if _RAW[0] else h.float()
         if not return_logits:
             raise NotImplementedError("only return_logits=True is used on the SPMM path (the loss is fused in SPMM.forward)")
         B, T, H = h.shape
@@ -285,4 +309,5 @@ class BertForMaskedLM(nn.Module):
             raise NotImplementedError("differentiable logits are produced inside ops.lm_head_loss; call under no_grad")
         V = self.config.vocab_size
         logits = ops.lm_logits(h.view(B * T, H), self.bert._bundles().head, V, self.logit_ld())
-        return logits.view(B, T, -1)[:, :, :V]
+        logits = logits.view(B, T, -1)[:, :, :V]
+        return logits if _RAW[0] else logits.float()

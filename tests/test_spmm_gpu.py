@@ -268,3 +268,48 @@ def test_fit_driver_runs_the_reference_hooks():
     assert int(model.queue_ptr) == (6 * 6) % model.queue_size
     assert int(model.optimizers().t_dev) == 6
     assert "loss_ita" in logged and "lr" in logged
+
+
+def test_smiles2pv_generation_matches_oracle():
+    """Config #4 (d_smiles2pv.py:14-52): 53 autoregressive property predictions through the sub-module API, against the
+    fp32 oracle restatement of the same loop.  bf16 activations feed back 53 times: |d| <= 5e-2 on O(1) values."""
+    from oracle import generate_ref
+    from spmm_b200 import generate
+    case = "tiny_b6"
+    g = load_golden(case)
+    ct, cp, _ = load_cfgs(case)
+    model = build_model(case)
+    ids, mask = g["ids"].to(DEV), g["mask"].to(DEV)
+    got = generate.smiles2pv(model, ids, mask)
+    P = oracle_state(g, device=DEV)
+    want = generate_ref.smiles2pv(P, ct, cp, ids, mask)
+    assert got.shape == want.shape == (ids.shape[0], 53) and got.dtype == torch.float32
+    print("smiles2pv max |d| %.3e (|want| max %.3f)" % (float((got - want).abs().max()), float(want.abs().max())))
+    assert float((got - want).abs().max()) <= 5e-2
+
+
+def test_pv2smiles_beam_search_runs_and_first_step_matches_oracle():
+    """Config #5 (d_pv2smiles_batched.py:24-59): the first decoder step's top-k tokens / log-probs against the oracle, and
+    the beam search itself terminates with k finished candidates that start with [CLS] and end with [SEP] (or runs out of
+    steps on a random-init model, in which case the unfinished list may be shorter)."""
+    from oracle import generate_ref
+    from spmm_b200 import generate
+    case = "tiny_b6"
+    g = load_golden(case)
+    ct, cp, _ = load_cfgs(case)
+    model = build_model(case)
+    model.eval()
+    pv = g["pv"][:1].to(DEV)
+    P = oracle_state(g, device=DEV)
+    text = torch.tensor([[2]], device=DEV)
+    want = torch.log_softmax(generate_ref.next_token_logits(P, ct, cp, pv, text), dim=-1)
+    property1 = model.property_embed(pv.unsqueeze(2))
+    props = torch.cat([model.property_cls.expand(1, -1, -1), property1], dim=1)
+    with torch.no_grad():
+        pe = model.property_encoder(inputs_embeds=props, return_dict=True).last_hidden_state
+        vals, idx = generate._next_token_logp(model, pe, text, 3, False)
+    assert float((vals[0] - want[0, idx[0]]).abs().max()) <= 3e-2
+    assert set(idx[0].tolist()) & set(torch.topk(want[0], 5).indices.tolist())
+    out = generate.pv2smiles(model, pv, k=2, max_steps=12)
+    for logp, toks in out:
+        assert int(toks[0]) == 2 and int(toks[-1]) == 3 and math.isfinite(logp)
