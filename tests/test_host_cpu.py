@@ -210,3 +210,32 @@ def test_lightning_shaped_hooks_follow_the_reference_schedule(monkeypatch):
     model.training_step(batch, 100)
     assert seen["alpha"][-2:] == [a, a]
     assert seen["sched"] == [0, 1, 2, 3 + 2]             # one step per epoch afterwards: epoch + warmup_steps
+
+
+def test_lightning_checkpoint_round_trip(tmp_path):
+    """`.ckpt` files carry the reference's state-dict surface (SPMM_pretrain.py:24-30, d_smiles2pv.py:132-143): a model
+    written and re-read is identical, queues keep the reference's [E, Q] layout on disk, and the d_*.py loading pattern
+    (queues dropped, no_train=True model, strict=False) reports no unexpected keys."""
+    from spmm_b200 import checkpoint, synth
+    from spmm_b200.SPMM_models import SPMM
+    g = load_golden("tiny_b6")
+    cfg = synth.pretrain_config(os.path.join(CFG, "config_tiny_text.json"), os.path.join(CFG, "config_tiny_property.json"), 96, 6)
+    torch.manual_seed(3)
+    m1 = SPMM(config=cfg)
+    m1.queue_ptr.fill_(12)
+    path = checkpoint.save(m1, str(tmp_path), epoch=4, global_step=1234)
+    assert os.path.basename(path) == "checkpoint_epoch=4.ckpt"
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    assert raw["epoch"] == 4 and raw["global_step"] == 1234
+    assert sorted((k, tuple(v.shape)) for k, v in raw["state_dict"].items()) == sorted((k, s) for k, s, _ in g["state_dict_keys"])
+    assert tuple(raw["state_dict"]["prop_queue"].shape) == (cfg["embed_dim"], 96)
+    torch.manual_seed(4)
+    m2 = SPMM(config=cfg)
+    msg, _ = checkpoint.load(m2, path)
+    assert not msg.missing_keys and not msg.unexpected_keys
+    s1, s2 = m1.state_dict(), m2.state_dict()
+    assert all(torch.equal(s1[k], s2[k]) for k in s1) and int(m2.queue_ptr) == 12
+    assert torch.equal(m2.prop_queue_km, m1.prop_queue_km)               # key-major storage restored from the [E, Q] view
+    m3 = SPMM(config=cfg, no_train=True)                                  # inference scripts
+    msg3, _ = checkpoint.load(m3, path, drop_queues=True)
+    assert not msg3.missing_keys and set(msg3.unexpected_keys) <= {"temp", "queue_ptr"}
