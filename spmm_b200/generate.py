@@ -2,7 +2,6 @@
 values, autoregressive over the property tokens) and d_pv2smiles_batched.py:17-59 + d_pv2smiles_single.py:26-51
 (property vector -> SMILES, beam search with k beams over the fusion decoder).  Host logic only: every encoder pass goes
 through the same sm_100a kernels as pre-training (no KV cache yet - SURVEY.md section 8f ranks that next)."""
-import numpy as np
 import torch
 
 
@@ -45,32 +44,37 @@ def _next_token_logp(model, prop_embeds, text, k, stochastic):
     return torch.log(top.values), top.indices
 
 
+def encode_properties(model, prop):
+    """[B, 53] property vectors -> PV-encoder states [B, 54, H] ([CLS] token + one embedded token per property)."""
+    tokens = torch.cat([model.property_cls.expand(prop.shape[0], -1, -1), model.property_embed(prop.unsqueeze(2))], dim=1)
+    return model.property_encoder(inputs_embeds=tokens, return_dict=True).last_hidden_state
+
+
 @torch.no_grad()
 def pv2smiles(model, prop, cls_id=2, sep_id=3, k=2, stochastic=False, max_steps=100):
-    """d_pv2smiles_batched.py:24-59 for ONE property vector `prop` [1, 53]: beam search with k beams; a beam that emits
-    [SEP] is moved to the finished list (its slot gets score -1e5), the search stops once k candidates are finished; no
-    length normalisation.  Returns the finished (log-prob, token ids incl. [CLS]/[SEP]) list, best first."""
+    """Beam search of d_pv2smiles_batched.py:24-59 for ONE property vector `prop` [1, 53].  Semantics kept from the
+    reference: every live beam is expanded by its k best (or k sampled) next tokens; from the second expansion on, a
+    candidate that ends in [SEP] moves to the finished list with its accumulated log-probability and is masked with
+    -1e5 in the live pool; the search stops as soon as k candidates are finished (or after `max_steps` expansions);
+    no length normalisation.  Returns up to k (log-prob, token ids incl. [CLS] ... [SEP]) pairs, best first."""
     model.eval()
-    dev = prop.device
-    property1 = model.property_embed(prop.unsqueeze(2))
-    properties = torch.cat([model.property_cls.expand(property1.size(0), -1, -1), property1], dim=1)
-    prop_embeds = model.property_encoder(inputs_embeds=properties, return_dict=True).last_hidden_state
-    product_input = torch.tensor([cls_id], device=dev).expand(1, 1)
-    values, indices = _next_token_logp(model, prop_embeds, product_input, k, stochastic)
-    product_input = torch.cat([torch.tensor([cls_id], device=dev).expand(k, 1), indices.squeeze(0).unsqueeze(-1)], dim=-1)
-    current_p = values.squeeze(0)
-    final_output = []
-    for _ in range(max_steps):
-        values, indices = _next_token_logp(model, prop_embeds, product_input, k, stochastic)
-        k2_p = current_p[:, None] + values
-        product_input_k2 = torch.cat([product_input.unsqueeze(1).repeat(1, k, 1), indices.unsqueeze(-1)], dim=-1)
-        if bool((indices == sep_id).any()):
-            for e in (indices == sep_id).nonzero(as_tuple=False):
-                final_output.append((float(k2_p[e[0], e[1]]), product_input_k2[e[0], e[1]].clone()))
-                k2_p[e[0], e[1]] = -1e5
-            if len(final_output) >= k:
-                break
-        current_p, flat = torch.topk(k2_p.flatten(), k)
-        rows, cols = np.unravel_index(flat.cpu().numpy(), tuple(k2_p.shape))
-        product_input = torch.stack([product_input_k2[r, c] for r, c in zip(rows, cols)], dim=0)
-    return sorted(final_output, key=lambda x: x[0], reverse=True)[:k]
+    enc = encode_properties(model, prop)
+    beams = torch.full((1, 1), cls_id, dtype=torch.long, device=prop.device)     # live prefixes [n_beams, T]
+    scores = torch.zeros(1, device=prop.device)
+    finished = []
+    for step in range(max_steps + 1):
+        logp, tok = _next_token_logp(model, enc, beams, k, stochastic)            # [n_beams, k] each
+        cand_scores = scores[:, None] + logp
+        cand = torch.cat([beams[:, None, :].expand(-1, k, -1), tok[:, :, None]], dim=-1)   # [n_beams, k, T + 1]
+        if step > 0:
+            ended = tok == sep_id
+            if bool(ended.any()):
+                for b, j in ended.nonzero(as_tuple=False).tolist():
+                    finished.append((float(cand_scores[b, j]), cand[b, j].clone()))
+                cand_scores = cand_scores.masked_fill(ended, -1e5)
+                if len(finished) >= k:
+                    break
+        scores, flat = cand_scores.flatten().topk(k)
+        beams = cand.flatten(0, 1)[flat]
+    finished.sort(key=lambda item: item[0], reverse=True)
+    return finished[:k]

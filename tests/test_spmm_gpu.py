@@ -303,10 +303,8 @@ def test_pv2smiles_beam_search_runs_and_first_step_matches_oracle():
     P = oracle_state(g, device=DEV)
     text = torch.tensor([[2]], device=DEV)
     want = torch.log_softmax(generate_ref.next_token_logits(P, ct, cp, pv, text), dim=-1)
-    property1 = model.property_embed(pv.unsqueeze(2))
-    props = torch.cat([model.property_cls.expand(1, -1, -1), property1], dim=1)
     with torch.no_grad():
-        pe = model.property_encoder(inputs_embeds=props, return_dict=True).last_hidden_state
+        pe = generate.encode_properties(model, pv)
         vals, idx = generate._next_token_logp(model, pe, text, 3, False)
     assert float((vals[0] - want[0, idx[0]]).abs().max()) <= 3e-2
     assert set(idx[0].tolist()) & set(torch.topk(want[0], 5).indices.tolist())
