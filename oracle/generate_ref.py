@@ -1,6 +1,8 @@
 """TEST INFRASTRUCTURE: fp32 restatement of the reference's SMILES->PV generation loop (d_smiles2pv.py:14-52) and of one
-PV->SMILES decoder step (d_pv2smiles_single.py:26-44) on the oracle's functional BERT (oracle/spmm_ref.py, pinned to the
-unmodified reference by tests/test_oracle.py).  Never imported by spmm_b200/."""
+PV->SMILES decoder step / beam search (d_pv2smiles_single.py:26-44, d_pv2smiles_batched.py:24-59) on the oracle's functional
+BERT (oracle/spmm_ref.py).  PINNED: tests/test_oracle.py::test_generation_oracle_matches_reference_golden checks it against
+tests/golden/generate_tiny.pt, recorded by executing the unmodified reference functions (oracle/make_golden_generate.py).
+Never imported by spmm_b200/."""
 import torch
 import torch.nn.functional as F
 
@@ -36,3 +38,30 @@ def next_token_logits(P, cfg_text, cfg_prop, pv, text):
     att = torch.where(text == 0, 0, 1)
     h = R.bert(P, "text_encoder.bert", cfg_text, ids=text, att=att, enc=prop_embeds.expand(text.shape[0], -1, -1), is_decoder=True)
     return R.lm_head(P, "text_encoder.cls.predictions", h)[:, -1, :]
+
+
+@torch.no_grad()
+def pv2smiles_beam(P, cfg_text, cfg_prop, pv, k=2, cls_id=2, sep_id=3, max_steps=100):
+    """d_pv2smiles_batched.py:24-59, deterministic branch: returns the finished (log-prob, ids) list, best first."""
+    def step(text):
+        lp = torch.log_softmax(next_token_logits(P, cfg_text, cfg_prop, pv, text), dim=-1)
+        top = torch.topk(lp, k=k, dim=-1)
+        return top.values, top.indices
+    beams = torch.full((1, 1), cls_id, dtype=torch.long, device=pv.device)
+    scores = torch.zeros(1, device=pv.device)
+    finished = []
+    for it in range(max_steps + 1):
+        logp, tok = step(beams)
+        cand_scores = scores[:, None] + logp
+        cand = torch.cat([beams[:, None, :].expand(-1, k, -1), tok[:, :, None]], dim=-1)
+        if it > 0:
+            ended = tok == sep_id
+            for b, j in ended.nonzero(as_tuple=False).tolist():
+                finished.append((float(cand_scores[b, j]), cand[b, j].clone()))
+            cand_scores = cand_scores.masked_fill(ended, -1e5)
+            if len(finished) >= k:
+                break
+        scores, flat = cand_scores.flatten().topk(k)
+        beams = cand.flatten(0, 1)[flat]
+    finished.sort(key=lambda x: x[0], reverse=True)
+    return finished[:k]

@@ -4,7 +4,9 @@ import pytest
 import torch
 
 from oracle import spmm_ref
-from tests.util import load_cfgs, load_golden, oracle_state, sample_idx
+import os
+
+from tests.util import REPO, load_cfgs, load_golden, oracle_state, sample_idx
 
 
 def _run(case):
@@ -59,3 +61,26 @@ def test_oracle_matches_reference_tiny():
 def test_oracle_matches_reference_full():
     torch.set_num_threads(8)
     _check("full_b8", 5e-5)
+
+
+def test_generation_oracle_matches_reference_golden():
+    """oracle/generate_ref.py (SMILES->PV loop, PV->SMILES decoder step and beam search) against
+    tests/golden/generate_tiny.pt, recorded by running the unmodified reference functions
+    (oracle/make_golden_generate.py).  fp32 on CPU: values to 1e-5, token ids exact."""
+    from oracle import generate_ref
+    gg = torch.load(os.path.join(REPO, "tests", "golden", "generate_tiny.pt"), weights_only=False)
+    g = load_golden("tiny_b6")
+    ct, cp, _ = load_cfgs("tiny_b6")
+    P = oracle_state(g, device="cpu")
+    got = generate_ref.smiles2pv(P, ct, cp, gg["ids"], gg["mask"])
+    assert torch.allclose(got, gg["smiles2pv"], atol=2e-5), float((got - gg["smiles2pv"]).abs().max())
+    with torch.no_grad():
+        P["text_encoder.cls.predictions.bias"][3] += gg["sep_bias"]      # the [SEP] nudge the golden run applied
+    for b in range(3):
+        pv = gg["pv"][b:b + 1]
+        lp = torch.log_softmax(generate_ref.next_token_logits(P, ct, cp, pv, torch.tensor([[2]])), dim=-1)
+        vals, idx = gg["first_step"][b]
+        assert torch.topk(lp[0], 5).indices.tolist() == idx.tolist()
+        assert torch.allclose(lp[0, idx], vals, atol=2e-5)
+        best = generate_ref.pv2smiles_beam(P, ct, cp, pv, k=2)[0][1].tolist()
+        assert best[:-1] == gg["beam_best"][b] and best[-1] == 3
