@@ -3,7 +3,9 @@
 // One CTA per (batch, head): the whole K/V of a head fits in shared memory, so softmax is single pass (no online
 // rescale) and the [B,12,Tq,Tk] probability tensor of the reference is never materialised; backward recomputes P
 // from the saved log-sum-exp.  Masks are generated in-kernel from kv_len (pad) and the causal flag.
-// Round-1 MMA path: warp-level mma.sync m16n8k16 bf16 (attention is ~1-2% of step FLOPs).
+// These are the round-0 warp-level mma.sync kernels.  The product path is attention_tc.cu (tcgen05 forward and backward);
+// this file keeps the C entry points, argument checks and - behind SPMM_ATTN_LEGACY=1, for A/B measurements only - the
+// old kernels.
 #include <cstdlib>
 
 #include "common.cuh"

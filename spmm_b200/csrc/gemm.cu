@@ -7,11 +7,14 @@
 // Operands may be K-major (row-major [rows][K]) or MN-major (row-major [K][rows]) so that
 // fwd (X.W^T), dgrad (dY.W) and wgrad (dY^T.X) all run without a transpose pass.
 //
-// Structure: persistent CTAs (one per SM), 256 threads:
+// Two kernels.  gemm2_bf16_kernel (below, "2-CTA kernel") carries the step: CTA pairs, 256 x 256 tiles,
+// cta_group::2 MMAs, 8 epilogue warps staging through shared memory into bulk tensor stores.  gemm_bf16_kernel<BN> is
+// the 1-CTA variant kept for M <= 128, N <= 128 and ragged N (e.g. the 300-column LM head):
+//   persistent CTAs (one per SM), 256 threads:
 //   warp 0 lane 0 : TMA producer      (smem full/empty ring, kStages deep)
 //   warp 1 lane 0 : tcgen05.mma issuer (accumulators double-buffered in TMEM: 2 x BN columns)
 //   warp 2        : TMEM alloc/dealloc
-//   warps 4..7    : epilogue (tcgen05.ld -> bias / GELU / dGELU / dropout / residual -> global)
+//   warps 4..7    : epilogue (tcgen05.ld -> bias / GELU / dGELU / dropout / residual -> global, row per thread)
 #include <cuda.h>
 #include <mutex>
 
