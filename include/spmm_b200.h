@@ -115,10 +115,12 @@ int spmm_scatter_add_rows_bf16(void* dst, const int* idx, const void* src, int n
  * the 8 similarity blocks, and returns
  * loss_ita, d loss/d z_prop, d loss/d z_text, d loss/d temp, plus the in-batch student sims
  * sim_i2t[B,B], sim_t2i[B,B] (for hard negatives, :157-158) and the normalised momentum feats (for enqueue).
- * Queues are stored key-major [Q][E] (the transpose of the reference's [E][Q] buffers). */
+ * Queues are stored key-major [Q][E] (the transpose of the reference's [E][Q] buffers).
+ * alpha_dev (device float, optional) overrides `alpha`: the distillation weight ramps every batch of epoch 0
+ * (SPMM_models.py:355), and a device scalar lets ONE captured CUDA graph of the step serve every value. */
 int spmm_itc_fwd_bwd(const float* z_prop, const float* z_text, const float* z_prop_m, const float* z_text_m,
-                     const float* prop_queue, const float* text_queue, const float* temp, float alpha, int B, int E,
-                     int Q, float* loss, float* dz_prop, float* dz_text, float* dtemp, float* sim_i2t, float* sim_t2i,
+                     const float* prop_queue, const float* text_queue, const float* temp, float alpha,
+                     const float* alpha_dev, int B, int E, int Q, float* loss, float* dz_prop, float* dz_text, float* dtemp, float* sim_i2t, float* sim_t2i,
                      float* feat_prop_m, float* feat_text_m, float* nan_flag, void* workspace, int64_t workspace_bytes,
                      void* stream);
 int64_t spmm_itc_workspace_bytes(int B, int E, int Q);
@@ -137,9 +139,13 @@ int spmm_enqueue(float* prop_queue, float* text_queue, const float* prop_feats, 
 /* ------------------------------------------------------------------ losses
  * LM: loss = (1-alpha) * CE(logits[:, :-1], ids[:, 1:]) (mean over ALL positions, PAD labels included)
  *          + alpha * mean_{label != 0} -sum softmax(teacher) * log_softmax(student)   (SPMM_models.py:233-238)
- * logits rows = b*L + t (ld elements, V valid); writes dlogits (bf16, zero for t = L-1). */
+ * logits rows = b*L + t (ld elements, V valid); writes dlogits (bf16, zero for t = L-1).
+ * alpha_dev (device float, optional) overrides alpha.  valid_len (device int, optional) = the batch's own padded
+ * width Lv <= L when rows are stored in a longer length bucket: positions t >= Lv-1 are ignored (zero gradient, not
+ * counted), so the result equals the reference's on the [B, Lv] batch (padding='longest', SPMM_models.py:352). */
 int spmm_lm_loss_fwd_bwd(const void* logits, const void* teacher_logits, int ld, const int64_t* ids, int B, int L,
-                         int V, float alpha, float* loss, void* dlogits, float* workspace, void* stream);
+                         int V, float alpha, const float* alpha_dev, const int* valid_len, float* loss, void* dlogits,
+                         float* workspace, void* stream);
 /* ITM (SPMM_models.py:201-206): logits = x[3B,2H] . W^T + b, CE with labels [1]*B + [0]*2B. */
 int spmm_itm_loss_fwd_bwd(const void* x, const float* w, const float* b, int n_rows, int n_pos, int D, float* loss,
                           void* dx, float* dw, float* db, void* stream);

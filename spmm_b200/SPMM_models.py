@@ -31,6 +31,19 @@ except Exception:                          # noqa: BLE001
     _Base = nn.Module
 
 
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def world_any(flag):
+    """MAX over the data-parallel world of a device flag (in place; a no-op on one rank).  The NaN guard of
+    SPMM_models.py:132 must be ONE decision for all replicas: the gathered queue rows and the all-reduced gradients are
+    global, so a rank that skipped its step alone would diverge from the others for good."""
+    if _world() > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    return flag
+
+
 def gather_world_feats(feats):
     """concat_all_gather (reference SPMM_models.py:389-399) for a stacked [2, B, E] feature tensor: ONE collective for
     both modalities; result [2, W*B, E] with rank r's rows at [r*B, (r+1)*B) exactly like torch.cat(tensors_gather)."""
@@ -54,7 +67,29 @@ class AttrDict(dict):
         self.__dict__ = self
 
 
-class SPMM(_Base):
+class _StandaloneHooks:
+    """What `pl.LightningModule` would provide to `training_step` (SPMM_models.py:348-386), for runs without
+    pytorch_lightning: `trainer.fit` attaches the optimiser / scheduler / logger and advances `current_epoch`."""
+    current_epoch = 0
+    global_rank = 0
+
+    def attach(self, optimizer, scheduler, global_rank=0, log=None):
+        self._opt, self._sched, self.global_rank = optimizer, scheduler, global_rank
+        self._log = log
+        return self
+
+    def optimizers(self):
+        return self._opt
+
+    def lr_schedulers(self):
+        return self._sched
+
+    def log(self, name, value, prog_bar=False):
+        if getattr(self, "_log", None) is not None:
+            self._log(name, value)
+
+
+class SPMM(*((_Base,) if _Base is not nn.Module else (_StandaloneHooks, nn.Module))):
     def __init__(self, tokenizer=None, config=None, loader_len=0, no_train=False):
         super().__init__()
         self.automatic_optimization = False
@@ -185,16 +220,21 @@ class SPMM(_Base):
         return self._arena
 
     # ------------------------------------------------------------------ the hot path
-    def forward(self, property_original, text_input_ids, text_attention_mask, alpha=0, mpm_mask=None, neg_idx=None):
+    def forward(self, property_original, text_input_ids, text_attention_mask, alpha=0, mpm_mask=None, neg_idx=None,
+                valid_len=None):
+        """`alpha` is a python number or a 1-element fp32 CUDA tensor (read by the loss kernels on the device, so one
+        captured CUDA graph serves the epoch-0 ramp).  `valid_len` (int32 CUDA scalar, optional): the batch's own
+        `padding='longest'` width when `text_input_ids` has been padded further to a graph length bucket."""
         from .xbert import raw_outputs
         with raw_outputs():                         # bf16 activations between the blocks of the hot path
-            return self._forward(property_original, text_input_ids, text_attention_mask, alpha, mpm_mask, neg_idx)
+            return self._forward(property_original, text_input_ids, text_attention_mask, alpha, mpm_mask, neg_idx, valid_len)
 
     @property
     def device(self):                               # LightningModule.device, read by d_smiles2pv.py:34
         return self.arena().device if self._arena is not None else next(self.parameters()).device
 
-    def _forward(self, property_original, text_input_ids, text_attention_mask, alpha=0, mpm_mask=None, neg_idx=None):
+    def _forward(self, property_original, text_input_ids, text_attention_mask, alpha=0, mpm_mask=None, neg_idx=None,
+                 valid_len=None):
         """Reference SPMM_models.py:79-256.  `mpm_mask` / `neg_idx=(neg_t2i, neg_i2t)` inject the random draws
         (parity tests); otherwise torch.bernoulli on the device and the counter-based sampler are used."""
         A = self.arena()
@@ -226,9 +266,13 @@ class SPMM(_Base):
             text_embeds_m = te_m.bert(ids, attention_mask=tmask, mode='text').last_hidden_state
             z_text_m = ops.proj_f32(text_embeds_m[:, 0, :], W["text_proj_m"])
         side = {}
+        if not torch.is_tensor(alpha):
+            alpha = float(alpha)
         loss_ita = ops.itc(z_prop, z_text, self.temp, z_prop_m, z_text_m, self.prop_queue_km, self.text_queue_km,
-                           float(alpha), side)                                                          # :102-131
-        nan_flag = side["nan_flag"]
+                           alpha, side)                                                                 # :102-131
+        # NaN guard (:132-133): one decision for the whole data-parallel world (enqueue, optimiser step and the returned
+        # losses all key off this flag), taken before anything global is touched
+        nan_flag = world_any(side["nan_flag"])
 
         # ================ ITM (:135-206) ================ #
         def fusion(q, q_mask, kv, kv_mask, dec=False):
@@ -260,7 +304,7 @@ class SPMM(_Base):
             h_m = te_m.bert(ids, attention_mask=tmask, encoder_hidden_states=prop_embeds_m, is_decoder=True).last_hidden_state
             logits_m = ops.lm_logits(h_m.view(-1, H), te_m.bert._bundles().head, V, te.logit_ld())
         h = te.bert(ids, attention_mask=tmask, encoder_hidden_states=prop_embeds, is_decoder=True).last_hidden_state
-        loss_mlm = ops.lm_head_loss(h.view(-1, H), logits_m, ids, te.bert._bundles().head, float(alpha), V)
+        loss_mlm = ops.lm_head_loss(h.view(-1, H), logits_m, ids, te.bert._bundles().head, alpha, V, valid_len)
 
         # ================ MPM (:240-254) ================ #
         pc = self.property_encoder(inputs_embeds=properties, is_decoder=True).last_hidden_state
@@ -293,39 +337,37 @@ class SPMM(_Base):
         assert self.queue_size % n == 0                                      # :279
         K.enqueue(self.prop_queue_km, self.text_queue_km, feats[0], feats[1], self.queue_ptr, skip_flag)
 
-    # ------------------------------------------------------------------ optimiser / Lightning-style hooks
     # ------------------------------------------------------------------ Lightning-shaped hooks (reference :345-386)
-    # pytorch_lightning is not a dependency: `trainer.fit` (spmm_b200/trainer.py) plays the Trainer and sets the handful of
-    # attributes these hooks read (optimizers / lr_schedulers / current_epoch / global_rank / log).
-    current_epoch = 0
-    global_rank = 0
-
-    def attach(self, optimizer, scheduler, global_rank=0, log=None):
-        self._opt, self._sched, self.global_rank = optimizer, scheduler, global_rank
-        self._log = log
-        self._stepper = None
-        return self
-
-    def optimizers(self):
-        return self._opt
-
-    def lr_schedulers(self):
-        return self._sched
-
-    def log(self, name, value, prog_bar=False):
-        if getattr(self, "_log", None) is not None:
-            self._log(name, value)
-
+    # With pytorch_lightning installed the class IS a LightningModule and `optimizers()`, `lr_schedulers()`, `log`,
+    # `current_epoch`, `global_rank` are Lightning's own; without it (this image) `_StandaloneHooks` supplies them and
+    # `trainer.fit` (spmm_b200/trainer.py) plays the Trainer.
     def lr_scheduler_step(self, scheduler, optimizer_idx, metric):       # reference :345-346 (manual optimisation)
         pass
 
+    def _graph_stepper(self, optimizer):
+        """The step's CUDA graph runner (trainer.GraphedTrainStep), built on first use; SPMM_EAGER=1 or
+        `model.use_cuda_graph = False` keeps the eager launches (debugging)."""
+        import os
+        from . import trainer
+        if not getattr(self, "use_cuda_graph", True) or os.environ.get("SPMM_EAGER") == "1":
+            return None
+        if not hasattr(optimizer, "prepare_step"):          # a stock torch optimizer cannot be captured (host-side state)
+            return None
+        st = self.__dict__.get("_stepper")
+        if st is None or st.opt is not optimizer:
+            st = trainer.GraphedTrainStep(self, optimizer)
+            self.__dict__["_stepper"] = st
+        return st
+
     def training_step(self, train_batch, batch_idx):
-        """Reference SPMM_models.py:348-380: tokenise, alpha ramp (epoch 0), forward/backward/clip/AdamW (one fused
-        `trainer.train_step`, or its CUDA graph), cosine schedule stepping with the reference's warm-up cadence.
+        """Reference SPMM_models.py:348-380: tokenise, alpha ramp (epoch 0), forward/backward/clip/AdamW - ONE replay of
+        the step's CUDA graph (alpha, lr and the batch's padded width are device scalars, so the ramp and
+        `padding='longest'` do not multiply graphs) - and the cosine schedule with the reference's warm-up cadence.
         Returns the four losses as ONE device tensor (no host sync; the reference's `loss != 0` NaN check is a device
-        flag that skips the optimiser step)."""
+        flag that skips the optimiser step on every rank)."""
         from . import trainer
         optimizer, scheduler = self.optimizers(), self.lr_schedulers()
+        optimizer = getattr(optimizer, "optimizer", optimizer)           # unwrap a LightningOptimizer
         prop, text = train_batch
         dev = self.arena().device
         if isinstance(text, (list, tuple)) and len(text) > 0 and isinstance(text[0], str):      # SMILES strings
@@ -335,8 +377,12 @@ class SPMM(_Base):
             ids, mask = text
         alpha = self.config['alpha'] if self.current_epoch > 0 else \
             self.config['alpha'] * min(1., batch_idx / max(self.loader_len, 1))
-        prop, ids, mask = prop.to(dev, non_blocking=True), ids.to(dev, non_blocking=True), mask.to(dev, non_blocking=True)
-        losses = torch.stack([l.detach() for l in trainer.train_step(self, optimizer, prop, ids, mask, alpha)])
+        stepper = self._graph_stepper(optimizer)
+        if stepper is not None:
+            losses = stepper(prop, ids, mask, alpha).clone()             # static output buffer -> this step's own copy
+        else:
+            prop, ids, mask = prop.to(dev, non_blocking=True), ids.to(dev, non_blocking=True), mask.to(dev, non_blocking=True)
+            losses = torch.stack([l.detach() for l in trainer.train_step(self, optimizer, prop, ids, mask, alpha)])
         if self.global_rank == 0:
             self.log('lr', optimizer.param_groups[0]["lr"], prog_bar=True)
             for name, l in zip(('loss_mlm', 'loss_mpm', 'loss_ita', 'loss_itm'), losses):

@@ -45,13 +45,13 @@ SIGNATURES = {
     "spmm_dgelu_bf16": (i32, [vp, vp, vp, i64, vp]),
     "spmm_gather_rows_bf16": (i32, [vp, vp, vp, i32, i64, vp]),
     "spmm_scatter_add_rows_bf16": (i32, [vp, vp, vp, i32, i64, vp]),
-    "spmm_itc_fwd_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+    "spmm_itc_fwd_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, f32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                i64, vp]),
     "spmm_itc_debug_trace": (i32, [vp]),
     "spmm_itc_workspace_bytes": (i64, [i32, i32, i32]),
     "spmm_sample_negatives": (i32, [vp, vp, i32, u64, u64, vp, vp, vp]),
     "spmm_enqueue": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]),
-    "spmm_lm_loss_fwd_bwd": (i32, [vp, vp, i32, vp, i32, i32, i32, f32, vp, vp, vp, vp]),
+    "spmm_lm_loss_fwd_bwd": (i32, [vp, vp, i32, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
     "spmm_itm_loss_fwd_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "spmm_mpm_loss_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "spmm_wordpiece_create": (vp, [C.POINTER(C.c_char_p), i32, i32, i32]),

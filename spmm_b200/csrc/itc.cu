@@ -575,10 +575,12 @@ __global__ void itc_combine_kernel(const float* part, float* lse, int splits, in
 // Loss, d/d temp and the chain rule through F.normalize.  One block; warp per student feature row (2B rows:
 // f_prop[b], f_text[b]); each row occurs once per key set.
 __global__ void __launch_bounds__(1024) itc_finish_kernel(const float* feats, const float* norms, const float* oacc,
-                                                           const float* lse, const float* temp, float alpha, int B,
+                                                           const float* lse, const float* temp, float alpha,
+                                                           const float* alpha_dev, int B,
                                                            int rows_pad, float* dz_prop, float* dz_text, float* loss,
                                                            float* dtemp, float* nan_flag) {
   __shared__ float sh[32];
+  if (alpha_dev != nullptr) alpha = __ldg(alpha_dev);   // device scalar: one captured graph serves the epoch-0 alpha ramp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const float inv_temp = 1.f / __ldg(temp);
   const float gscale = inv_temp / (2.f * B);
@@ -698,7 +700,8 @@ extern "C" int64_t spmm_itc_workspace_bytes(int B, int E, int Q) {
 
 extern "C" int spmm_itc_fwd_bwd(const float* z_prop, const float* z_text, const float* z_prop_m, const float* z_text_m,
                                 const float* prop_queue, const float* text_queue, const float* temp,
-                                float alpha, int B, int E, int Q, float* loss, float* dz_prop, float* dz_text,
+                                float alpha, const float* alpha_dev, int B, int E, int Q, float* loss, float* dz_prop,
+                                float* dz_text,
                                 float* dtemp, float* sim_i2t, float* sim_t2i, float* feat_prop_m, float* feat_text_m,
                                 float* nan_flag, void* workspace, int64_t workspace_bytes, void* stream) {
   SPMM_ARG(z_prop && z_text && z_prop_m && z_text_m && temp);
@@ -771,7 +774,7 @@ extern "C" int spmm_itc_fwd_bwd(const float* z_prop, const float* z_text, const 
   SPMM_CHECK_LAUNCH();
   itc_scan_kernel<2><<<grid, IT_THREADS, IT_SMEM, st>>>(maps, a);
   SPMM_CHECK_LAUNCH();
-  itc_finish_kernel<<<1, 1024, 0, st>>>(feats, norms, oacc, lse, temp, alpha, B, pl.rows_pad, dz_prop, dz_text, loss, dtemp,
+  itc_finish_kernel<<<1, 1024, 0, st>>>(feats, norms, oacc, lse, temp, alpha, alpha_dev, B, pl.rows_pad, dz_prop, dz_text, loss, dtemp,
                                         nan_flag);
   SPMM_CHECK_LAUNCH();
   return 0;

@@ -8,12 +8,15 @@
 namespace spmm {
 
 // ------------------------------------------------------------------ LM loss
+// `valid_len` (device scalar, optional): the batch's own padded width Lv <= L (= its longest sequence).  Rows are
+// stored with stride L (a CUDA-graph length bucket); positions t >= Lv - 1 are bucket padding the reference never saw:
+// they get zero gradient and do not count in the CE mean over B * (Lv - 1) positions.
 __global__ void lm_count_kernel(const int64_t* __restrict__ ids, int B, int L, float* ws) {
   __shared__ float sh[32];
   float c = 0.f;
   for (int i = threadIdx.x; i < B * (L - 1); i += blockDim.x) {
     const int b = i / (L - 1), t = i % (L - 1);
-    c += (ids[(size_t)b * L + t + 1] != 0) ? 1.f : 0.f;   // labels != 0, SPMM_models.py:237
+    c += (ids[(size_t)b * L + t + 1] != 0) ? 1.f : 0.f;   // labels != 0, SPMM_models.py:237 (bucket padding is id 0)
   }
   c = block_sum(c, sh);
   if (threadIdx.x == 0) { ws[0] = c; ws[1] = 0.f; ws[2] = 0.f; }
@@ -23,13 +26,15 @@ constexpr int LM_MAXV = 320;  // per-lane register budget: 10 logits
 
 __global__ void __launch_bounds__(256)
 lm_loss_kernel(const __nv_bfloat16* __restrict__ logits, const __nv_bfloat16* __restrict__ teacher, int ld,
-               const int64_t* __restrict__ ids, int B, int L, int V, float alpha, float* ws,
-               __nv_bfloat16* __restrict__ dlogits) {
+               const int64_t* __restrict__ ids, int B, int L, int V, float alpha, const float* __restrict__ alpha_dev,
+               const int* __restrict__ valid_len, float* ws, __nv_bfloat16* __restrict__ dlogits) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= B * L) return;
+  if (alpha_dev != nullptr) alpha = __ldg(alpha_dev);
+  const int Lv = valid_len != nullptr ? min(max(__ldg(valid_len), 2), L) : L;
   const int b = row / L, t = row % L;
   __nv_bfloat16* drow = dlogits + (size_t)row * ld;
-  if (t == L - 1) {  // sliced away by [:, :-1] -> zero gradient
+  if (t >= Lv - 1) {  // sliced away by [:, :-1] (or bucket padding) -> zero gradient
     for (int c = lane; c < ld; c += 32) drow[c] = f2bf(0.f);
     return;
   }
@@ -67,7 +72,7 @@ lm_loss_kernel(const __nv_bfloat16* __restrict__ logits, const __nv_bfloat16* __
     atomicAdd(ws + 1, ce);
     if (valid) atomicAdd(ws + 2, distill);
   }
-  const float w_ce = (1.f - alpha) / (float)(B * (L - 1));
+  const float w_ce = (1.f - alpha) / (float)(B * (Lv - 1));
   const float w_ds = valid ? alpha / n_valid : 0.f;
 #pragma unroll
   for (int i = 0; i < LM_MAXV / 32; ++i) {
@@ -82,8 +87,11 @@ lm_loss_kernel(const __nv_bfloat16* __restrict__ logits, const __nv_bfloat16* __
   }
 }
 
-__global__ void lm_final_kernel(const float* ws, int B, int L, float alpha, float* loss) {
-  *loss = (1.f - alpha) * ws[1] / (float)(B * (L - 1)) + alpha * ws[2] / ws[0];
+__global__ void lm_final_kernel(const float* ws, int B, int L, float alpha, const float* alpha_dev, const int* valid_len,
+                                float* loss) {
+  if (alpha_dev != nullptr) alpha = *alpha_dev;
+  const int Lv = valid_len != nullptr ? min(max(*valid_len, 2), L) : L;
+  *loss = (1.f - alpha) * ws[1] / (float)(B * (Lv - 1)) + alpha * ws[2] / ws[0];
 }
 
 // ------------------------------------------------------------------ ITM head + CE (single CTA; ~1 MFLOP)
@@ -207,17 +215,18 @@ __global__ void mpm_final_kernel(const float* ws, float* loss) { *loss = 5.f * w
 using namespace spmm;
 
 extern "C" int spmm_lm_loss_fwd_bwd(const void* logits, const void* teacher_logits, int ld, const int64_t* ids, int B,
-                                    int L, int V, float alpha, float* loss, void* dlogits, float* workspace,
-                                    void* stream) {
+                                    int L, int V, float alpha, const float* alpha_dev, const int* valid_len,
+                                    float* loss, void* dlogits, float* workspace, void* stream) {
   SPMM_ARG(logits && teacher_logits && ids && loss && dlogits && workspace && B > 0 && L > 1 && V > 0 && V <= LM_MAXV &&
            ld >= V);
   cudaStream_t st = (cudaStream_t)stream;
   lm_count_kernel<<<1, 256, 0, st>>>(ids, B, L, workspace);
   SPMM_CHECK_LAUNCH();
   lm_loss_kernel<<<(B * L + 7) / 8, 256, 0, st>>>((const __nv_bfloat16*)logits, (const __nv_bfloat16*)teacher_logits, ld,
-                                                  ids, B, L, V, alpha, workspace, (__nv_bfloat16*)dlogits);
+                                                  ids, B, L, V, alpha, alpha_dev, valid_len, workspace,
+                                                  (__nv_bfloat16*)dlogits);
   SPMM_CHECK_LAUNCH();
-  lm_final_kernel<<<1, 1, 0, st>>>(workspace, B, L, alpha, loss);
+  lm_final_kernel<<<1, 1, 0, st>>>(workspace, B, L, alpha, alpha_dev, valid_len, loss);
   SPMM_CHECK_LAUNCH();
   return 0;
 }

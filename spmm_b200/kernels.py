@@ -131,7 +131,16 @@ def scatter_add_rows(dst, idx, src):
     call("spmm_scatter_add_rows_bf16", dst.data_ptr(), idx.data_ptr(), src.data_ptr(), src.shape[0], src[0].numel(), _st())
 
 
+def _scalar_or_dev(alpha):
+    """(host float, device pointer or None): a CUDA tensor is read by the kernel itself (graph-replay safe)."""
+    if torch.is_tensor(alpha):
+        assert alpha.is_cuda and alpha.dtype == torch.float32 and alpha.numel() == 1
+        return 0.0, alpha.data_ptr()
+    return float(alpha), None
+
+
 def itc(z_prop, z_text, z_prop_m, z_text_m, prop_queue, text_queue, temp, alpha):
+    """`alpha`: python float, or a 1-element fp32 CUDA tensor read on the device."""
     B, E = z_prop.shape
     Q = prop_queue.shape[0]
     dev = z_prop.device
@@ -143,7 +152,7 @@ def itc(z_prop, z_text, z_prop_m, z_text_m, prop_queue, text_queue, temp, alpha)
                feat_prop_m=torch.empty(B, E, **f32), feat_text_m=torch.empty(B, E, **f32),
                nan_flag=torch.empty((), **f32))
     call("spmm_itc_fwd_bwd", z_prop.data_ptr(), z_text.data_ptr(), z_prop_m.data_ptr(), z_text_m.data_ptr(),
-         prop_queue.data_ptr(), text_queue.data_ptr(), temp.data_ptr(), float(alpha), B, E, Q, out["loss"].data_ptr(),
+         prop_queue.data_ptr(), text_queue.data_ptr(), temp.data_ptr(), *_scalar_or_dev(alpha), B, E, Q, out["loss"].data_ptr(),
          out["dz_prop"].data_ptr(), out["dz_text"].data_ptr(), out["dtemp"].data_ptr(), out["sim_i2t"].data_ptr(),
          out["sim_t2i"].data_ptr(), out["feat_prop_m"].data_ptr(), out["feat_text_m"].data_ptr(),
          out["nan_flag"].data_ptr(), ws.data_ptr(), ws_bytes, _st())
@@ -165,14 +174,18 @@ def enqueue(prop_queue, text_queue, prop_feats, text_feats, queue_ptr, skip_flag
          queue_ptr.data_ptr(), prop_feats.shape[0], E, Q, _p(skip_flag), _st())
 
 
-def lm_loss(logits, teacher, ids, V, alpha):
+def lm_loss(logits, teacher, ids, V, alpha, valid_len=None):
+    """`alpha` float or 1-element fp32 CUDA tensor; `valid_len` optional int32 CUDA scalar: the batch's own padded width
+    when `ids` sits in a longer length bucket (positions beyond it are ignored)."""
     B, L = ids.shape
     ld = logits.stride(0)
     loss = torch.empty((), device=logits.device, dtype=torch.float32)
     dlogits = torch.empty_like(logits)
     ws = torch.empty(4, device=logits.device, dtype=torch.float32)
-    call("spmm_lm_loss_fwd_bwd", logits.data_ptr(), teacher.data_ptr(), ld, ids.data_ptr(), B, L, V, float(alpha),
-         loss.data_ptr(), dlogits.data_ptr(), ws.data_ptr(), _st())
+    if valid_len is not None:
+        assert valid_len.is_cuda and valid_len.dtype == torch.int32 and valid_len.numel() == 1
+    call("spmm_lm_loss_fwd_bwd", logits.data_ptr(), teacher.data_ptr(), ld, ids.data_ptr(), B, L, V, *_scalar_or_dev(alpha),
+         _p(valid_len), loss.data_ptr(), dlogits.data_ptr(), ws.data_ptr(), _st())
     return loss, dlogits
 
 

@@ -13,8 +13,7 @@ Weight gradients are accumulated by the wgrad GEMMs straight into the flat fp32 
 the functions therefore return gradients only for activations.  `anchor` is a dummy requires-grad scalar that keeps
 a backward node alive for functions whose only differentiable inputs are parameters.
 
-tests/ monkeypatch the public names below with oracle/torch_ops.py to check the wiring on CPU; the product path
-has no fallback.
+The product path has no fallback: every function here launches kernels from libspmm_b200.so.
 """
 import math
 from types import SimpleNamespace
@@ -352,7 +351,7 @@ def lm_logits(h, W, V, ld):
 
 class _LmHeadLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h, logits_m, ids, W, alpha, V):
+    def forward(ctx, h, logits_m, ids, W, alpha, V, valid_len):
         M, H = h.shape
         ld = logits_m.shape[1]
         pre = torch.empty(M, H, device=h.device, dtype=BF16)
@@ -360,7 +359,7 @@ class _LmHeadLoss(torch.autograd.Function):
         t, mean, rstd = K.layernorm_fwd(a, W.ln_g, W.ln_b, W.eps)
         logits = torch.empty(M, ld, device=h.device, dtype=BF16)
         K.gemm(t, W.wdec, M, V, H, bias=W.bdec, out=logits)
-        loss, dlogits = K.lm_loss(logits, logits_m, ids, V, alpha)
+        loss, dlogits = K.lm_loss(logits, logits_m, ids, V, alpha, valid_len)
         ctx.save_for_backward(h, pre, a, t, mean, rstd, dlogits)
         ctx.W, ctx.V = W, V
         return loss
@@ -379,12 +378,13 @@ class _LmHeadLoss(torch.autograd.Function):
         dpre = K.dgelu(da, pre)
         K.colsum(dpre, W.g_bt)
         _wgrad(dpre, h, W.g_wt, H, H, M)
-        return K.gemm(dpre, W.wt, M, H, H, b_mn=True), None, None, None, None, None
+        return K.gemm(dpre, W.wt, M, H, H, b_mn=True), None, None, None, None, None, None
 
 
-def lm_head_loss(h, logits_m, ids, W, alpha, V):
-    """LM head + (1-alpha) CE + alpha distillation (SPMM_models.py:224-238) on h [B*L, H]."""
-    return _LmHeadLoss.apply(h, logits_m, ids, W, alpha, V)
+def lm_head_loss(h, logits_m, ids, W, alpha, V, valid_len=None):
+    """LM head + (1-alpha) CE + alpha distillation (SPMM_models.py:224-238) on h [B*L, H].  `alpha` may be a device
+    scalar; `valid_len` (device int32) marks bucket padding beyond the batch's own width."""
+    return _LmHeadLoss.apply(h, logits_m, ids, W, alpha, V, valid_len)
 
 
 class _ItmLoss(torch.autograd.Function):

@@ -23,10 +23,12 @@ class FusedClipAdamW(torch.optim.Optimizer):
         self.t = 0
         # The step counter lives on the device (t_dev, advanced by a 1-thread kernel that also derives the bias
         # corrections), so a captured CUDA graph of the step picks up fresh values on every replay and a host that runs
-        # ahead of the GPU cannot race the per-step scalars.  Only lr comes from the host (scheduler), through pinned
-        # memory; `t` is the host-side mirror (state_dict, schedulers).
-        self.lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        # ahead of the GPU cannot race the per-step scalars.  lr comes from the host (scheduler): whenever it changes,
+        # `prepare_step` issues a stream-ordered fill of `lr_dev` (the value travels as a kernel argument, so a host
+        # that runs several steps ahead cannot overwrite it before the GPU has read it - no pinned staging buffer).
+        # `t` is the host-side mirror (state_dict, schedulers).
         self.lr_dev = torch.zeros(1, dtype=torch.float32, device=self.A.device)
+        self._lr_published = None
         self.t_dev = torch.zeros(1, dtype=torch.int64, device=self.A.device)
         self.hyper_dev = torch.zeros(3, dtype=torch.float32, device=self.A.device)
 
@@ -35,11 +37,14 @@ class FusedClipAdamW(torch.optim.Optimizer):
         self.A.zero_grad()
 
     def prepare_step(self):
-        """Host side of a step: advance the host mirror of t and publish lr to pinned memory.  Called once per step
-        BEFORE the (possibly graph-replayed) device work."""
+        """Host side of a step: advance the host mirror of t and, if the scheduler changed it, publish lr to the device
+        (stream-ordered fill).  Called once per step BEFORE the (possibly graph-replayed) device work, outside capture."""
         grp = self.param_groups[0]
         self.t += 1
-        self.lr_host[0] = grp["lr"]
+        lr = float(grp["lr"])
+        if lr != self._lr_published:
+            self.lr_dev.fill_(lr)
+            self._lr_published = lr
 
     @torch.no_grad()
     def step(self, closure=None, skip_flag=None, grad_scale=1.0, prepared=False):
@@ -47,7 +52,6 @@ class FusedClipAdamW(torch.optim.Optimizer):
         grp = self.param_groups[0]
         if not prepared:
             self.prepare_step()
-        self.lr_dev.copy_(self.lr_host, non_blocking=True)
         K.adam_tick(self.t_dev, self.lr_dev, self.hyper_dev, grp["betas"][0], grp["betas"][1], skip_flag)
         K.grad_sumsq(A.G[g0:], A.sumsq)
         K.adamw(A.P[g0:], A.G[g0:], self.exp_avg, self.exp_avg_sq, grp["lr"], grp["betas"][0], grp["betas"][1], grp["eps"],

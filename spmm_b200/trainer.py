@@ -34,20 +34,31 @@ def train_step(model, optimizer, prop, text_input_ids, text_attention_mask, alph
 
 
 class GraphedTrainStep:
-    """The whole training step as ONE CUDA graph per (batch shape, alpha): ~2000 kernel launches replayed without the
-    Python / launch overhead (the eager step spends ~56 ms of host time enqueuing 61 ms of GPU work).
+    """The whole training step as ONE CUDA graph per batch SHAPE: ~1500 kernel launches replayed without the Python /
+    launch overhead (the eager step spends ~56 ms of host time enqueuing ~45 ms of GPU work).
 
-    Possible because the step has no host sync: negatives are sampled on the device, queue_ptr and the NaN guard live on
-    the device, and everything that changes per step lives there too: the dropout / sampler salt and Adam's step
-    counter (with its bias corrections) are advanced by kernels inside the graph; only lr is copied from pinned memory.  New batches are copied into static input
-    buffers.  `alpha` is baked into a graph; a new value (epoch-0 ramp, SPMM_models.py:355) captures another graph or,
-    with `max_graphs` exceeded, falls back to the eager step.
+    Possible because the step has no host sync and everything that changes per step lives on the device: negatives are
+    sampled there, queue_ptr and the (world-wide) NaN guard are device scalars, the dropout / sampler salt and Adam's
+    step counter are advanced by kernels inside the graph, and `alpha` (ramped every batch of epoch 0,
+    SPMM_models.py:355), `lr` and the batch's own padded width are device scalars filled before each replay.
+
+    `padding='longest'` gives every batch its own width L (SPMM_models.py:352): batches are padded further to the next
+    multiple of `len_bucket` so that a few graphs cover all widths; the pad columns are masked keys / dead rows, and
+    the LM loss ignores them through `valid_len`, so the losses equal those of the [B, L] batch.  Graphs share one
+    memory pool (they never run concurrently) and are evicted least-recently-used beyond `max_graphs`.
     """
 
-    def __init__(self, model, optimizer, max_graphs=4, warmup_steps=2):
+    def __init__(self, model, optimizer, max_graphs=16, warmup_steps=2, len_bucket=8):
+        import collections
         self.model, self.opt = model, optimizer
-        self.graphs = {}
-        self.max_graphs, self.warmup_steps = max_graphs, warmup_steps
+        self.graphs = collections.OrderedDict()
+        self.max_graphs, self.warmup_steps, self.len_bucket = max_graphs, warmup_steps, len_bucket
+        dev = model.arena().device
+        self.alpha_dev = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.valid_len = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.losses = torch.zeros(4, device=dev, dtype=torch.float32)     # static output, outside the graphs' pool
+        self.pool = None
+        self.captures = 0
 
     def _snapshot(self):
         m, o, A = self.model, self.opt, self.model.arena()
@@ -66,47 +77,76 @@ class GraphedTrainStep:
         ops.step_rng(A.device).reset(s["salt"])
         torch.cuda.set_rng_state(s["rng"], A.device)
 
+    def bucket_len(self, L):
+        b = self.len_bucket
+        return L if b <= 1 else (L + b - 1) // b * b
+
+    def _fill(self, st, prop, ids, mask, alpha, mpm_mask):
+        """Batch -> the graph's static input buffers (async; pinned host tensors are copied without a sync)."""
+        L = ids.shape[1]
+        st["prop"].copy_(prop, non_blocking=True)
+        if L == st["ids"].shape[1]:
+            st["ids"].copy_(ids, non_blocking=True)
+            st["mask"].copy_(mask, non_blocking=True)
+        else:                                   # bucket padding: id 0 ([PAD]) / mask 0 beyond the batch's own width
+            st["ids"].zero_(); st["mask"].zero_()
+            st["ids"][:, :L].copy_(ids, non_blocking=True)
+            st["mask"][:, :L].copy_(mask, non_blocking=True)
+        if mpm_mask is not None:
+            st["mpm"].copy_(mpm_mask, non_blocking=True)
+        self.alpha_dev.fill_(float(alpha))      # kernel argument, stream-ordered: no pinned-memory race
+        self.valid_len.fill_(int(L))
+
     def _capture(self, key, prop, ids, mask, alpha, mpm_mask):
-        from . import ops
         dev = self.model.arena().device
-        st = {"prop": prop.to(dev, copy=True), "ids": ids.to(dev, copy=True), "mask": mask.to(dev, copy=True),
-              "mpm": None if mpm_mask is None else mpm_mask.to(dev, copy=True)}
-        kw = {} if mpm_mask is None else {"mpm_mask": st["mpm"]}
-        snap = self._snapshot()                             # warm-up steps are real steps: undo them afterwards
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(self.warmup_steps):              # lazy allocations / kernel attributes happen here
-                train_step(self.model, self.opt, st["prop"], st["ids"], st["mask"], alpha, **kw)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self._restore(snap)
+        B, Lb = key[0], key[1]
+        st = {"prop": torch.zeros((B,) + tuple(prop.shape[1:]), device=dev, dtype=torch.float32),
+              "ids": torch.zeros((B, Lb), device=dev, dtype=torch.int64),
+              "mask": torch.zeros((B, Lb), device=dev, dtype=torch.int64),
+              "mpm": None if mpm_mask is None else torch.zeros(tuple(mpm_mask.shape), device=dev, dtype=torch.float32)}
+        self._fill(st, prop, ids, mask, alpha, mpm_mask)
+        kw = {"valid_len": self.valid_len}
+        if mpm_mask is not None:
+            kw["mpm_mask"] = st["mpm"]
+        if self.captures == 0 and self.warmup_steps > 0:
+            # lazy allocations / kernel attributes happen in eager warm-up steps; they are real steps: undo them afterwards
+            snap = self._snapshot()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup_steps):
+                    train_step(self.model, self.opt, st["prop"], st["ids"], st["mask"], self.alpha_dev, **kw)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._restore(snap)
+            del snap
+        if self.pool is None:
+            self.pool = torch.cuda.graph_pool_handle()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            losses = train_step(self.model, self.opt, st["prop"], st["ids"], st["mask"], alpha, _prepared=True, **kw)
-            st["losses"] = torch.stack([l.detach() for l in losses])
+        with torch.cuda.graph(g, pool=self.pool):
+            losses = train_step(self.model, self.opt, st["prop"], st["ids"], st["mask"], self.alpha_dev, _prepared=True, **kw)
+            self.losses.copy_(torch.stack([l.detach() for l in losses]))
         st["graph"] = g
+        self.captures += 1
+        while len(self.graphs) >= self.max_graphs:          # LRU eviction: the pool memory is reused by later captures
+            self.graphs.popitem(last=False)
         self.graphs[key] = st
         return st
 
     def __call__(self, prop, ids, mask, alpha, mpm_mask=None):
+        """One training step on the batch; returns the 4 losses (static device tensor, overwritten by the next call)."""
         from . import ops
-        key = (tuple(prop.shape), tuple(ids.shape), float(alpha), mpm_mask is not None)
+        key = (prop.shape[0], self.bucket_len(ids.shape[1]), mpm_mask is not None)
         st = self.graphs.get(key)
         if st is None:
-            if len(self.graphs) >= self.max_graphs:
-                kw = {} if mpm_mask is None else {"mpm_mask": mpm_mask}
-                return torch.stack([l.detach() for l in train_step(self.model, self.opt, prop, ids, mask, alpha, **kw)])
             st = self._capture(key, prop, ids, mask, alpha, mpm_mask)
-        st["prop"].copy_(prop, non_blocking=True)
-        st["ids"].copy_(ids, non_blocking=True)
-        st["mask"].copy_(mask, non_blocking=True)
-        if mpm_mask is not None:
-            st["mpm"].copy_(mpm_mask, non_blocking=True)
+        else:
+            self.graphs.move_to_end(key)
+            self._fill(st, prop, ids, mask, alpha, mpm_mask)
         ops.step_rng(self.model.arena().device).host += 1
         self.opt.prepare_step()
         st["graph"].replay()
-        return st["losses"]
+        return self.losses
 
 
 def fit(model, loader, max_epochs=1, log=None):
@@ -121,6 +161,6 @@ def fit(model, loader, max_epochs=1, log=None):
     for epoch in range(max_epochs):
         model.current_epoch = epoch
         for batch_idx, batch in enumerate(loader):
-            model.training_step(batch, batch_idx)
+            model.training_step(batch, batch_idx)       # one CUDA-graph replay per batch (SPMM._graph_stepper)
         history.append(model.on_train_epoch_end())
     return history

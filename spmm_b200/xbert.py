@@ -9,6 +9,7 @@ parameter arena (spmm_b200/arena.py).  Activations are bf16 [tokens, hidden].
 """
 import contextlib
 import json
+import os
 from types import SimpleNamespace
 
 import torch
@@ -47,12 +48,33 @@ class BertConfig:
         return dict(self.__dict__)
 
 
+def _validation_enabled():
+    """Input validation costs a host sync, so it runs where a sync is acceptable: inference (grad disabled) and
+    whenever SPMM_CHECK_INPUTS=1; never inside a CUDA-graph capture.  SPMM_CHECK_INPUTS=0 turns it off everywhere."""
+    env = os.environ.get("SPMM_CHECK_INPUTS")
+    if env == "0":
+        return False
+    if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+        return False
+    return env == "1" or not torch.is_grad_enabled()
+
+
 class MaskInfo:
-    """A right-padded 0/1 attention mask reduced to what the kernels consume: per-sequence valid lengths."""
+    """A right-padded 0/1 attention mask reduced to what the kernels consume: per-sequence valid lengths.
+
+    The reference honours arbitrary masks (xbert.py:889-948); the kernels here take prefix lengths, which is what
+    `padding='longest'` produces.  A mask that is not of prefix form (left padding, holes) would silently mask the wrong
+    keys, so it is rejected where validation runs (`_validation_enabled`)."""
 
     def __init__(self, mask=None, kv_len=None):
         self.mask = mask
         if kv_len is None and mask is not None:
+            if mask.dim() != 2:
+                raise ValueError("attention masks must be [batch, length] 0/1 tensors, got shape %s" % (tuple(mask.shape),))
+            if mask.shape[1] > 1 and _validation_enabled():
+                if not bool((mask[:, 1:] <= mask[:, :-1]).all()):
+                    raise ValueError("spmm_b200 kernels need right-padded (prefix-form) attention masks: every row must be "
+                                     "1...1 0...0; got a mask with a hole or left padding")
             kv_len = mask.sum(dim=1).to(torch.int32)
         self.kv_len = kv_len
 
@@ -228,6 +250,12 @@ class BertModel(nn.Module):
             raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
         if input_ids is not None:
             B, T = input_ids.shape
+            if T > cfg.max_position_embeddings:
+                raise ValueError("sequence length %d exceeds max_position_embeddings %d" % (T, cfg.max_position_embeddings))
+            if _validation_enabled() and input_ids.numel() > 0:
+                lo, hi = int(input_ids.min()), int(input_ids.max())
+                if lo < 0 or hi >= cfg.vocab_size:
+                    raise IndexError("token id out of range [0, %d): min %d max %d" % (cfg.vocab_size, lo, hi))
             x = ops.embed_text(input_ids.contiguous(), bd.emb, p_hid, bd.anchor)
         elif inputs_embeds is not None:
             B, T = inputs_embeds.shape[:2]

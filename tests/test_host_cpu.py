@@ -154,8 +154,11 @@ def _dist_worker(rank, world, path, out):
     # gradient all-reduce + 1/world scale as in trainer.train_step
     grad = torch.full((5,), float(rank + 1))
     dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+    # the NaN guard is one decision for the whole world: a flag raised on rank 1 only must be seen by rank 0
+    from spmm_b200.SPMM_models import world_any
+    flag = world_any(torch.tensor(1.0 if rank == 1 else 0.0))
     if rank == 0:
-        torch.save({"g": g, "grad": grad / world}, out)
+        torch.save({"g": g, "grad": grad / world, "flag": flag}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -170,6 +173,7 @@ def test_data_parallel_plumbing_gloo_world2(tmp_path):
     want = torch.cat([base, base + 100], dim=1)             # torch.cat(tensors_gather, dim=0) per modality
     assert torch.equal(r["g"], want)
     assert torch.equal(r["grad"], torch.full((5,), 1.5))
+    assert float(r["flag"]) == 1.0
     # queue divisibility rule of the reference (SPMM_models.py:279) for W in {1,2,4,8} at B=96
     assert all(36864 % (96 * w) == 0 for w in (1, 2, 4, 8))
 
@@ -239,3 +243,56 @@ def test_lightning_checkpoint_round_trip(tmp_path):
     m3 = SPMM(config=cfg, no_train=True)                                  # inference scripts
     msg3, _ = checkpoint.load(m3, path, drop_queues=True)
     assert not msg3.missing_keys and set(msg3.unexpected_keys) <= {"temp", "queue_ptr"}
+
+
+def test_attention_masks_must_be_right_padded():
+    """The kernels consume prefix lengths; the reference honours arbitrary masks (xbert.py:889-948).  A mask with a hole
+    or left padding is rejected where validation runs (inference / SPMM_CHECK_INPUTS=1) instead of masking the wrong keys."""
+    from spmm_b200.xbert import MaskInfo
+    ok = torch.tensor([[1, 1, 1, 0], [1, 0, 0, 0], [1, 1, 1, 1]])
+    with torch.no_grad():
+        assert MaskInfo(ok).kv_len.tolist() == [3, 1, 4]
+        for bad in (torch.tensor([[0, 1, 1, 1]]), torch.tensor([[1, 0, 1, 0]])):
+            with pytest.raises(ValueError):
+                MaskInfo(bad)
+    assert MaskInfo(kv_len=torch.tensor([2, 3])).kv_len.tolist() == [2, 3]
+    with pytest.raises(ValueError):
+        MaskInfo(torch.ones(2, 3, 4))
+
+
+def test_graph_stepper_buckets_lengths_and_keeps_lru_order():
+    """GraphedTrainStep keys its graphs on (batch, bucketed length, injected-mask flag) - never on alpha or lr, which
+    are device scalars - and evicts least-recently-used graphs.  Host logic only (capture is stubbed)."""
+    from types import SimpleNamespace
+    from spmm_b200 import trainer
+    g = trainer.GraphedTrainStep.__new__(trainer.GraphedTrainStep)
+    import collections
+    g.graphs, g.max_graphs, g.len_bucket = collections.OrderedDict(), 2, 8
+    assert [g.bucket_len(L) for L in (1, 8, 9, 63, 64, 65, 99)] == [8, 8, 16, 64, 64, 72, 104]
+    captured, filled = [], []
+
+    def fake_capture(key, *a):
+        captured.append(key)
+        while len(g.graphs) >= g.max_graphs:
+            g.graphs.popitem(last=False)
+        g.graphs[key] = {"graph": SimpleNamespace(replay=lambda: None)}
+        return g.graphs[key]
+    g._capture = fake_capture
+    g._fill = lambda st, *a: filled.append(a[3])
+    g.model = SimpleNamespace(arena=lambda: SimpleNamespace(device="cpu"))
+    g.opt = SimpleNamespace(prepare_step=lambda: None)
+    g.losses = torch.zeros(4)
+    import spmm_b200.ops as ops
+    orig = ops.step_rng
+    ops.step_rng = lambda dev: SimpleNamespace(host=0)
+    try:
+        pv = torch.zeros(6, 53)
+        for L, alpha in ((60, 0.0), (64, 0.1), (57, 0.2), (70, 0.3), (62, 0.4), (99, 0.4), (70, 0.4)):
+            g(pv, torch.zeros(6, L, dtype=torch.long), torch.zeros(6, L, dtype=torch.long), alpha)
+    finally:
+        ops.step_rng = orig
+    # 60/64/57/62 share the 64-bucket; 70 -> 72; 99 -> 104 evicts the least recently used (72: the 64-bucket was just
+    # replayed for L=62); the second L=70 batch captures 72 again and evicts 64
+    assert captured == [(6, 64, False), (6, 72, False), (6, 104, False), (6, 72, False)]
+    assert list(g.graphs) == [(6, 104, False), (6, 72, False)]
+    assert filled == [0.1, 0.2, 0.4]                   # replays refresh the device scalars; alpha never keys a graph
