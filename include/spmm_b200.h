@@ -159,8 +159,9 @@ int spmm_mpm_loss_fwd_bwd(const void* t, const float* w, const float* b, const f
  * the reference); optionally emits the bf16 shadows of p and p_m used by the GEMMs. */
 int spmm_ema_multi(const float* p, float* p_m, void* p_bf16, void* p_m_bf16, int64_t n, float momentum,
                    float one_minus_momentum, void* stream);
-/* clip_grad_norm_(5.) + AdamW (SPMM_models.py:340,361-362).  sumsq_out[0] receives sum g^2. */
-int spmm_grad_sumsq(const float* g, int64_t n, float* sumsq_out, void* stream);
+/* clip_grad_norm_(5.) + AdamW (SPMM_models.py:340,361-362).  sumsq_out[0] receives sum g^2, added in a fixed order
+ * (bit-identical on every data-parallel replica).  workspace: >= 1024 floats, zero before first use (left zeroed). */
+int spmm_grad_sumsq(const float* g, int64_t n, float* sumsq_out, float* workspace, void* stream);
 /* t_dev += 1 (unless *skip_flag != 0) and hyper_dev = {*lr_dev, 1-beta1^t, sqrt(1-beta2^t)} computed on the device */
 int spmm_adam_tick(long long* t_dev, const float* lr_dev, float* hyper_dev, float beta1, float beta2,
                    const float* skip_flag, void* stream);

@@ -311,7 +311,8 @@ class SPMM(*((_Base,) if _Base is not nn.Module else (_StandaloneHooks, nn.Modul
         po = fusion(pc, None, text_embeds, tmask, dec=True)
         loss_mpm = ops.mtr_head_loss(po.view(-1, H), pv, mpm_mask, W["mtr"])      # already x5 (:256)
 
-        self.last_aux = {"neg_t2i": neg_t2i, "neg_i2t": neg_i2t, "nan_flag": nan_flag, "mpm_mask": mpm_mask}
+        self.last_aux = {"neg_t2i": neg_t2i, "neg_i2t": neg_i2t, "nan_flag": nan_flag, "mpm_mask": mpm_mask,
+                         "feat_prop_m": side["feat_prop_m"], "feat_text_m": side["feat_text_m"]}
         # NaN guard (:132-133) without a host sync: zero losses, and the flag disables enqueue + optimiser step
         bad = nan_flag > 0
         zero = torch.zeros((), device=pv.device)

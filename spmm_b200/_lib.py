@@ -58,7 +58,7 @@ SIGNATURES = {
     "spmm_wordpiece_destroy": (None, [vp]),
     "spmm_wordpiece_encode_batch": (i32, [vp, C.POINTER(C.c_char_p), i32, i32, i32, i32, i32, vp, vp, i32]),
     "spmm_ema_multi": (i32, [vp, vp, vp, vp, i64, f32, f32, vp]),
-    "spmm_grad_sumsq": (i32, [vp, i64, vp, vp]),
+    "spmm_grad_sumsq": (i32, [vp, i64, vp, vp, vp]),
     "spmm_adam_tick": (i32, [vp, vp, vp, f32, f32, vp, vp]),
     "spmm_adamw_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp, vp, vp]),
 }

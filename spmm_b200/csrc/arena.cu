@@ -40,8 +40,13 @@ __global__ void __launch_bounds__(256) cast_kernel(const float4* __restrict__ s,
   }
 }
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ g, int64_t n4, float* out) {
+// sum g^2 with a FIXED summation order: per-CTA partials, then the last CTA to finish (ticket counter) adds them in
+// index order.  Data-parallel replicas hold bit-identical reduced gradients, so they compute the bit-identical clip
+// coefficient and their weights never drift apart (a float atomicAdd per CTA made the total depend on arrival order).
+__global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ g, int64_t n4, float* out,
+                                                    float* __restrict__ partials, unsigned int* ticket) {
   __shared__ float sh[32];
+  __shared__ bool last;
   float acc = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -49,7 +54,18 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ g
     acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
   }
   acc = block_sum(acc, sh);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = acc;
+    __threadfence();
+    last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;   // wraps to 0: ready for the next call
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(partials + i);
+  t = block_sum(t, sh);
+  if (threadIdx.x == 0) *out = t;
 }
 
 // torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.AdamW.step (decoupled decay).
@@ -214,12 +230,12 @@ extern "C" int spmm_cast_f32_to_bf16(const float* src, void* dst, int64_t n, voi
   return 0;
 }
 
-extern "C" int spmm_grad_sumsq(const float* g, int64_t n, float* sumsq_out, void* stream) {
-  SPMM_ARG(g && sumsq_out && n >= 0 && n % 4 == 0 && ((uintptr_t)g & 15) == 0);
-  cudaError_t e = cudaMemsetAsync(sumsq_out, 0, sizeof(float), (cudaStream_t)stream);
-  if (e != cudaSuccess) return (int)e;
-  if (n == 0) return 0;
-  sumsq_kernel<<<flat_grid(n / 4, 4), 256, 0, (cudaStream_t)stream>>>((const float4*)g, n / 4, sumsq_out);
+extern "C" int spmm_grad_sumsq(const float* g, int64_t n, float* sumsq_out, float* workspace, void* stream) {
+  SPMM_ARG(g && sumsq_out && workspace && n >= 0 && n % 4 == 0 && ((uintptr_t)g & 15) == 0);
+  if (n == 0) return (int)cudaMemsetAsync(sumsq_out, 0, sizeof(float), (cudaStream_t)stream);
+  // workspace: [0] ticket counter (zero before first use, the kernel leaves it zero), [1 ..] per-CTA partials
+  sumsq_kernel<<<flat_grid(n / 4, 4), 256, 0, (cudaStream_t)stream>>>((const float4*)g, n / 4, sumsq_out, workspace + 1,
+                                                                      reinterpret_cast<unsigned int*>(workspace));
   SPMM_CHECK_LAUNCH();
   return 0;
 }

@@ -209,8 +209,15 @@ def mpm_loss(t, w, b, pv, mpm_mask, dw, db):
     return loss, dt
 
 
+_SUMSQ_WS = {}
+
+
 def grad_sumsq(g, out):
-    call("spmm_grad_sumsq", g.data_ptr(), g.numel(), out.data_ptr(), _st())
+    """out[0] = sum g^2 with a fixed summation order (replicas get the bit-identical clip coefficient)."""
+    ws = _SUMSQ_WS.get(g.device)
+    if ws is None:
+        ws = _SUMSQ_WS[g.device] = torch.zeros(1024, device=g.device, dtype=torch.float32)
+    call("spmm_grad_sumsq", g.data_ptr(), g.numel(), out.data_ptr(), ws.data_ptr(), _st())
 
 
 def adam_tick(t_dev, lr_dev, hyper_dev, beta1, beta2, skip_flag=None):

@@ -1,0 +1,136 @@
+"""Parity at the configuration bench.py measures (BASELINE.json configs[1]): reference config_bert*.json shapes,
+B = 96 molecules, full 36 864-entry queues - the CUDA `SPMM` step against the fp32 oracle (oracle/spmm_ref.py, pinned
+to the unmodified reference by tests/test_oracle.py) on the same name-seeded weights, the same injected Bernoulli mask
+and the same injected negatives.  Two batches: fixed SMILES length 64 (the bench default; head-pair attention tiles,
+several tiles per persistent CTA) and ragged lengths U{12..99} padded to the longest (`bench.py --ragged`).
+
+Tolerances = BASELINE.md section 5: losses |d| <= 1e-2; per-tensor gradient rel-L2 <= 3e-2 and cosine >= 0.999; global
+gradient rel-L2 <= 1.5e-2; d/d temp <= 1e-1 (ill-conditioned w.r.t. bf16 feature noise); EMA bit-exact; queue rows as
+enqueued by the reference (SPMM_models.py:79-256, 271-286)."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests.util import CFG  # noqa: E402
+
+DEV = "cuda"
+B, Q = 96, 36864
+
+
+def _build():
+    from spmm_b200 import synth
+    from spmm_b200.SPMM_models import SPMM
+    tj, pj = os.path.join(CFG, "config_bert.json"), os.path.join(CFG, "config_bert_property.json")
+    model = SPMM(config=synth.pretrain_config(tj, pj, queue_size=Q, batch_size=B))
+    synth.fill_by_name(model)
+    model.to(DEV)
+    model.build_arenas(DEV)
+    model.eval()
+    return model, json.load(open(tj)), json.load(open(pj))
+
+
+@pytest.mark.parametrize("ragged", [False, True], ids=["fixed64", "ragged"])
+def test_whole_step_matches_oracle_at_bench_config(ragged):
+    from oracle import spmm_ref
+    from spmm_b200 import synth
+    model, ct, cp = _build()
+    pv, ids, mask, lens = synth.synthetic_batch(B, seed=1234, fixed_len=None if ragged else 64)
+    g = torch.Generator().manual_seed(77)
+    mpm = (torch.rand(B, 53, generator=g) < 0.5).float()
+    shift = torch.randint(1, B, (2, B), generator=g)
+    neg = [((torch.arange(B) + shift[i]) % B).tolist() for i in range(2)]          # never the positive itself
+    pv, ids, mask, mpm = pv.to(DEV), ids.to(DEV), mask.to(DEV), mpm.to(DEV)
+    P = spmm_ref.state_from_model(model, device=DEV)                                # oracle state BEFORE the step (EMA, queues)
+    losses = model(pv, ids, mask, alpha=0.4, mpm_mask=mpm, neg_idx=neg)
+    sum(losses).backward()
+    ol, aux = spmm_ref.forward(P, ct, cp, pv, ids, mask, 0.4, mpm, neg_t2i=neg[0], neg_i2t=neg[1])
+    sum(ol).backward()
+    got = torch.stack([l.detach().double().cpu() for l in losses])
+    want = torch.stack([l.detach().double().cpu() for l in ol])
+    print("L=%d losses ours %s oracle %s" % (ids.shape[1], got.tolist(), want.tolist()))
+    assert torch.all((got - want).abs() <= 1e-2), (got, want)
+    assert float(model.last_aux["nan_flag"]) == 0.0
+    # side effects: EMA bit-exact, queue rows, pointer
+    params = dict(model.named_parameters())
+    n_ema = 0
+    for k, p in params.items():
+        if k.split(".")[0].endswith("_m"):
+            assert torch.equal(p.detach(), P[k]), k
+            n_ema += p.numel()
+    assert n_ema == 143775020
+    assert int(model.queue_ptr) == aux["queue_ptr"] == B
+    assert torch.allclose(model.prop_queue[:, :B], P["prop_queue"][:, :B], atol=2e-2)
+    assert torch.allclose(model.text_queue[:, :B], P["text_queue"][:, :B], atol=2e-2)
+    assert torch.equal(model.prop_queue[:, B:], P["prop_queue"][:, B:])
+    # gradients: every tensor
+    num = den = 0.0
+    bad, worst = [], (0.0, None)
+    gn = float(sum(float(P[k].grad.double().pow(2).sum()) for k in params if params[k].grad is not None) ** 0.5)
+    for n, p in params.items():
+        if p.grad is None:
+            continue
+        a, b = p.grad.detach().float().flatten(), P[n].grad.flatten()
+        num += float((a - b).double().pow(2).sum())
+        den += float(b.double().pow(2).sum())
+        if float(b.norm()) < 1e-5 * gn:
+            continue                                                                # mathematically-zero (key biases)
+        rel = float((a - b).norm() / b.norm())
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+        if n != "temp" and rel > worst[0]:
+            worst = (rel, n)
+        if rel > (1e-1 if n == "temp" else 3e-2) or cos < 0.999:
+            bad.append((n, rel, cos))
+    print("global grad norm %.4f  global rel-L2 %.3e  worst tensor %s  d temp ours %.5f oracle %.5f" % (
+        gn, (num / den) ** 0.5, worst, float(model.temp.grad), float(P["temp"].grad)))
+    assert not bad, bad[:10]
+    assert (num / den) ** 0.5 <= 1.5e-2
+    assert params["property_encoder.embeddings.word_embeddings.weight"].grad is None
+
+
+def test_graphed_training_step_on_bucketed_lengths_equals_eager_step():
+    """`SPMM.training_step` replays the step's CUDA graph on a batch padded to a length bucket (trainer.GraphedTrainStep);
+    alpha, lr and the batch's own width are device scalars.  Same model, eval mode, injected PV mask, full shapes at a
+    small batch: losses and first-step gradients must equal the eager step on the UNPADDED batch, for two different
+    widths served by the same graph and two alphas."""
+    from spmm_b200 import ops, synth, trainer
+    from spmm_b200.SPMM_models import SPMM
+    from spmm_b200.optim import FusedClipAdamW
+    tj, pj = os.path.join(CFG, "config_bert.json"), os.path.join(CFG, "config_bert_property.json")
+    Bs = 8
+    batches = []
+    for seed, L in ((5, 59), (6, 62)):
+        pv, ids, mask, _ = synth.synthetic_batch(Bs, seed=seed, min_len=20, max_len=L + 1)
+        assert ids.shape[1] <= 64
+        batches.append((pv.to(DEV), ids.to(DEV), mask.to(DEV)))
+    mpm = (torch.rand(Bs, 53, generator=torch.Generator().manual_seed(3)) < 0.5).float().to(DEV)
+    out = {}
+    for mode in ("eager", "graph"):
+        model = SPMM(config=synth.pretrain_config(tj, pj, queue_size=96 * 4, batch_size=Bs))
+        synth.fill_by_name(model)
+        model.to(DEV)
+        model.build_arenas(DEV)
+        model.eval()
+        opt = FusedClipAdamW(model, lr=1e-4, weight_decay=0.02)
+        ops.step_rng(DEV).reset(0)
+        stepper = trainer.GraphedTrainStep(model, opt) if mode == "graph" else None
+        hist, grads = [], []
+        for (pv, ids, mask), alpha in zip(batches, (0.1, 0.4)):
+            if stepper is None:
+                l = torch.stack([x.detach() for x in trainer.train_step(model, opt, pv, ids, mask, alpha, mpm_mask=mpm)])
+            else:
+                l = stepper(pv, ids, mask, alpha, mpm_mask=mpm).clone()
+            hist.append(l.cpu())
+            grads.append(model.arena().G.clone())
+        out[mode] = (torch.stack(hist), grads, int(model.queue_ptr), None if stepper is None else len(stepper.graphs))
+    print("eager", out["eager"][0].tolist())
+    print("graph", out["graph"][0].tolist())
+    assert out["graph"][3] == 1                                  # both widths (<= 64) share ONE graph
+    assert torch.allclose(out["eager"][0], out["graph"][0], atol=2e-3)
+    ge, gg = out["eager"][1][0], out["graph"][1][0]
+    print("step-1 gradient rel-L2 eager (unpadded) vs graph (bucket-padded): %.2e" % float((ge - gg).norm() / ge.norm()))
+    assert float((ge - gg).norm() / ge.norm()) < 1e-3
+    assert out["eager"][2] == out["graph"][2]

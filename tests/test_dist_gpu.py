@@ -1,0 +1,35 @@
+"""Multi-GPU numerical parity of the data-parallel step on real GPUs (run with `gpurun --gpus 2`): launches
+tests/dist_gpu_worker.py under torchrun on 2 ranks (NCCL) and checks its verdict.  Skipped on a 1-GPU box."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_step_reduces_gradients_and_keeps_replicas_bit_identical(tmp_path):
+    out = str(tmp_path / "dist2.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(REPO, "tests", "dist_gpu_worker.py"), out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=REPO)
+    print(r.stdout[-3000:])
+    print(r.stderr[-3000:])
+    assert r.returncode == 0
+    res = json.load(open(out))
+    keep = os.environ.get("SPMM_DIST_TEST_LOG")                  # e.g. profiles/r2_dist2_parity.json
+    if keep:
+        json.dump(res, open(keep, "w"), indent=1)
+    assert res["world"] == 2 and res["nccl"] == "nccl"
+    assert res["grad_mean_rel"] < 1e-5, res["grad_mean_rel"]     # float-atomic summation order between two backward runs
+    assert res["grad_differs_from_local_rel"] > 1e-2              # the check is not vacuous: ranks hold different batches
+    assert res["weights_moved"] and res["queue_rank_major"] and res["finite"]
+    assert res["queue_ptr_after_1"] == 16 and res["queue_ptr_final"] == (5 * 16) % (8 * 2 * 6) and res["t_dev"] == 5
+    for tag in ("identical_after_3_eager_steps", "identical_after_2_graph_steps"):
+        assert all(res[tag].values()), (tag, res[tag])

@@ -259,7 +259,15 @@ def ref_attention(q, k, v, kv_len, causal, scale):
 @pytest.mark.parametrize("B,h,Tq,Tk,causal,ragged", [(4, 12, 54, 54, False, False), (3, 12, 99, 99, True, True),
                                                      (5, 2, 54, 83, False, True), (2, 12, 83, 54, False, False),
                                                      (2, 12, 128, 128, True, True), (3, 2, 17, 64, False, True),
-                                                     (2, 12, 54, 54, True, False)])
+                                                     (2, 12, 54, 54, True, False),
+                                                     # the benchmarked geometry (B = 96 and the 3B ITM passes, 12 heads):
+                                                     # 576-3456 tiles on 148 persistent CTAs, so every CTA walks >= 4
+                                                     # head-pair tiles (TMEM double-buffer phase wrap, TMA ring wrap)
+                                                     (96, 12, 64, 64, False, False), (96, 12, 64, 64, True, True),
+                                                     (96, 12, 54, 54, False, False), (96, 12, 54, 64, False, True),
+                                                     (96, 12, 64, 54, False, False), (96, 12, 99, 99, True, True),
+                                                     (288, 12, 54, 64, False, True), (288, 12, 64, 54, False, False),
+                                                     (288, 12, 64, 64, False, True)])
 def test_attention_fwd_bwd(B, h, Tq, Tk, causal, ragged):
     H = h * 64
     self_attn = Tq == Tk
@@ -372,7 +380,10 @@ def test_itc_matches_oracle(B, Q):
         abs(float(out["dtemp"]) - float(tr.grad)) / abs(float(tr.grad))))
     assert abs(float(out["loss"]) - float(loss)) < 4e-3
     assert rel_err(out["dz_prop"], zp.grad) < 1e-3 and rel_err(out["dz_text"], zt.grad) < 1e-3
-    assert abs(float(out["dtemp"]) - float(tr.grad)) < 5e-3 * abs(float(tr.grad)) + 1e-5
+    # d/d temp: <= 1e-3 at the benchmarked size; <= 5e-3 for the small cases, where fewer rows
+    # average the TF32 operand rounding of this near-cancelling sum (CPU emulation: 0.7-1.8e-3)
+    dtemp_tol = 1e-3 if (B, Q) == (96, 36864) else 5e-3
+    assert abs(float(out["dtemp"]) - float(tr.grad)) < dtemp_tol * abs(float(tr.grad)) + 1e-5
     assert torch.allclose(out["sim_i2t"], s_i2t[:, :B].detach(), atol=1e-4)
     assert torch.allclose(out["sim_t2i"], s_t2i[:, :B].detach(), atol=1e-4)
     assert torch.allclose(out["feat_prop_m"], F.normalize(z[2], dim=-1), atol=1e-6)
