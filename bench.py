@@ -9,11 +9,16 @@ the reference's config_bert*.json shapes with B=96 molecules per GPU, queue 3686
 tensor-core GEMMs with fp32 master weights, synthetic BPE-300 ids + N(0,1) property vectors, name-seeded weights.
 N>1 is launched by torchrun (one rank per GPU, NCCL); weak scaling (per-GPU batch fixed).
 
-Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` feeds pinned HOST
-batches through the public API each step and reads the losses back.  `roofline` is for the dominant kernel (the
-tcgen05 GEMM, tensor-bound) measured with CUDA events around every launch of one extra instrumented step;
-`cpu_baseline` is the oracle port of the reference path timed on the host cores on a bounded sample.
-`--impl reference` times that CPU path alone (the reference's own algorithm; /root/reference is not on the GPU box).
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM (replays of the step's CUDA
+graph); `e2e` goes through the reference-facing hook `SPMM.training_step((pv, list_of_SMILES_strings), batch_idx)`:
+WordPiece tokenisation, H2D copies of the pinned host batch, graph replay, scheduler cadence and a D2H read of the
+four losses are all inside the timed region.  `roofline` is for the dominant kernel (the tcgen05 GEMM, tensor-bound):
+every GEMM launch of the step is timed INSIDE a replay of the step's graph with in-kernel %globaltimer stamps (first
+CTA past its dependency wait -> last CTA exit), so the figure is the kernel's exposed time in the real step, not an
+eager launch bracketed by events.  `cpu_baseline` is the oracle port of the reference path timed on the host cores on a
+bounded sample; `gpu_eager_baseline` is the same port on this GPU under torch.autocast(bfloat16) - what the reference's
+'16-mixed' eager PyTorch path would run.
+`--impl reference` times the CPU path alone (the reference's own algorithm; /root/reference is not on the GPU box).
 """
 import argparse
 import json
@@ -29,6 +34,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 CFG = os.path.join(REPO, "spmm_b200", "configs")
 H, I, E, P_TOK, V = 768, 3072, 256, 54, 300
+GEMM_DRAM_BYTES_PER_LAUNCH = None      # filled from profiles/r2_launches_dram.csv once captured (see kernel_rooflines)
 
 
 def flops_per_molecule(l, B, Q):
@@ -98,19 +104,30 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU baseline (oracle port)
-def cpu_reference_steps(steps, warmup, batch, seq_len, ragged, queue=36864):
-    """Times the reference algorithm (oracle/spmm_ref.py, pinned to the unmodified reference by tests/test_oracle.py)
-    on the host cores: fp32, train-step body = forward + backward + clip + AdamW.  Returns (molecules/s, ms/step, cores)."""
+def cpu_reference_steps(steps, warmup, batch, seq_len, ragged, queue=36864, device="cpu"):
+    """Times the reference algorithm (oracle/spmm_ref.py, pinned to the unmodified reference by tests/test_oracle.py):
+    train-step body = zero_grad + forward + backward + clip + AdamW, eager PyTorch.  device="cpu": fp32 on the host cores.
+    device="cuda": the same code on this GPU under torch.autocast(bfloat16) (the reference's '16-mixed' path; 2B
+    multinomial(...).item() host syncs and all), CUDA-event timed.  Returns (molecules/s, ms/step, cores)."""
+    import contextlib
     import torch
     from oracle import spmm_ref
     from spmm_b200 import synth
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    on_gpu = device != "cpu"
+    if not on_gpu:
+        torch.set_num_threads(cores)
     ct = json.load(open(os.path.join(CFG, "config_bert.json")))
     cp = json.load(open(os.path.join(CFG, "config_bert_property.json")))
     keys = torch.load(os.path.join(REPO, "tests", "golden", "full_b8.pt"), weights_only=False)["state_dict_keys"]
     keys = [(k, (s if not k.endswith("queue") else (s[0], queue)), d) for k, s, d in keys]
-    P = synth.state_from_keys(keys)
+    P0 = synth.state_from_keys(keys)
+    P, moved = {}, {}
+    for k, v in P0.items():                                   # aliases (tied decoder) keep sharing one tensor
+        if id(v) not in moved:
+            moved[id(v)] = v.to(device)
+        P[k] = moved[id(v)]
+    del P0, moved
     frozen = ("property_encoder_m.", "text_encoder_m.", "property_proj_m.", "text_proj_m.")
     leaves, seen = [], set()
     for k, v in P.items():
@@ -120,19 +137,30 @@ def cpu_reference_steps(steps, warmup, batch, seq_len, ragged, queue=36864):
             leaves.append(v)
     opt = torch.optim.AdamW(leaves, lr=5e-5, weight_decay=0.02)
     pv, ids, mask, _ = synth.synthetic_batch(batch, seed=1234, fixed_len=None if ragged else seq_len)
+    pv, ids, mask = pv.to(device), ids.to(device), mask.to(device)
     times, ptr = [], 0
     for it in range(warmup + steps):
+        if on_gpu:
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         t0 = time.perf_counter()
         opt.zero_grad()
         mpm = torch.bernoulli(torch.full_like(pv, 0.5))
-        losses, aux = spmm_ref.forward(P, ct, cp, pv, ids, mask, 0.4, mpm, queue_ptr=ptr,
-                                       sampler=lambda wt, wi: ([int(torch.multinomial(w, 1)) for w in wt],
-                                                               [int(torch.multinomial(w, 1)) for w in wi]))
+        with (torch.autocast("cuda", dtype=torch.bfloat16) if on_gpu else contextlib.nullcontext()):
+            losses, aux = spmm_ref.forward(P, ct, cp, pv, ids, mask, 0.4, mpm, queue_ptr=ptr,
+                                           sampler=lambda wt, wi: ([int(torch.multinomial(w, 1)) for w in wt],
+                                                                   [int(torch.multinomial(w, 1)) for w in wi]))
         ptr = aux["queue_ptr"]
         sum(losses).backward()
         torch.nn.utils.clip_grad_norm_(leaves, 5.0)
         opt.step()
-        dt = time.perf_counter() - t0
+        if on_gpu:
+            e1.record()
+            torch.cuda.synchronize()
+            dt = e0.elapsed_time(e1) / 1e3
+        else:
+            dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     ms = 1e3 * statistics.median(times)
@@ -144,14 +172,17 @@ def run_reference(args):
     if rank != 0:
         return
     B = 8
-    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    steps, warmup = max(5, min(args.steps, 8)), 2          # bounded sample: ~1.5 s per step on 16 cores
     val, ms, cores = cpu_reference_steps(steps, warmup, B, args.seq_len, args.ragged)
     line = {"impl": "reference", "metric": "pretrain molecules/sec", "value": val, "unit": "molecules/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, B, 1),
             "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": cores, "kind": "port",
-                             "sample": "%d timed step(s) of batch %d (full queue 36864, fp32, fwd+bwd+clip+AdamW) on the host cores" % (steps, B)},
+                             "sample": "median of %d timed steps (after %d warm-ups) of batch %d, full queue 36864, fp32 "
+                                       "fwd+bwd+clip+AdamW on the host cores; oracle/spmm_ref.py = the PORT of the reference's "
+                                       "algorithm pinned to the unmodified reference by golden vectors (the reference itself needs "
+                                       "pre-import shims and is not on the GPU box)" % (steps, warmup, B)},
             "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -181,6 +212,27 @@ def workload_config(args, B, world):
                         % (B, "ragged SMILES lengths U{12..99}" if args.ragged else "SMILES length %d" % args.seq_len),
             "global_batch": B * world, "seq_len": None if args.ragged else args.seq_len, "parallelism": "dp%d" % world,
             "l2": "working set per step (0.58 GB bf16 weights + 2.9 GB fp32 arenas + activations) >> 126 MB L2; no explicit flush"}
+
+
+def synthetic_smiles(tok, lens, seed):
+    """SMILES-alphabet strings whose WordPiece encoding has exactly lens[b] model-input tokens ([CLS] pieces [SEP]),
+    built with the tokenizer itself (greedy longest-match merges make the piece count depend on the characters)."""
+    import random
+    rnd = random.Random(seed)
+    alphabet = "CCCCccccNnOo()()==12345#SFl"
+    out = []
+    for L in lens:
+        s, n_pieces = "[CLS]", int(L) - 2
+        while True:
+            cand = s + rnd.choice(alphabet)
+            n = int(tok([cand], pin_memory=False).attention_mask.sum()) - 3      # minus HF [CLS], '[CLS]' piece, [SEP]
+            if n > n_pieces:
+                continue
+            s = cand
+            if n == n_pieces:
+                break
+        out.append(s)
+    return out
 
 
 # ------------------------------------------------------------------------------------------- our arm
@@ -214,7 +266,7 @@ def run_ours(args):
     model.to(dev)
     model.build_arenas(dev)
     model.train()
-    opt = FusedClipAdamW(model, lr=5e-5, weight_decay=0.02)
+    (opt,), (sched,) = model.configure_optimizers()          # FusedClipAdamW(lr 5e-5, wd 0.02, clip 5.0) + cosine schedule
     ops.manual_seed(999 + rank)
     torch.manual_seed(999 + rank)
     pv_h, ids_h, mask_h, lens = synth.synthetic_batch(B, seed=1234 + rank, fixed_len=None if args.ragged else args.seq_len)
@@ -228,6 +280,15 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     graphed = None if args.eager else trainer.GraphedTrainStep(model, opt)
+    # the public hook: SPMM.training_step((pv, SMILES strings), batch_idx) - reference SPMM_models.py:348-380
+    from spmm_b200.tokenizer import WordPieceTokenizer
+    model.tokenizer = WordPieceTokenizer(os.path.join(CFG, "vocab_bpe_300.txt"), do_lower_case=False, do_basic_tokenize=False)
+    smiles = synthetic_smiles(model.tokenizer, lens, 4321 + rank)
+    model.attach(opt, sched, global_rank=rank, log=None)
+    model.current_epoch, model.loader_len = 1, 1000          # past the epoch-0 ramp: alpha = 0.4 like the resident loop
+    model.use_cuda_graph = graphed is not None
+    if graphed is not None:
+        model.__dict__["_stepper"] = graphed                 # training_step replays the same graph as the resident loop
 
     def step_eager():
         return trainer.train_step(model, opt, pv, ids, mask, alpha)
@@ -237,11 +298,12 @@ def run_ours(args):
             return step_eager()
         return graphed(pv, ids, mask, alpha)
 
+    e2e_idx = [1]
+
     def step_e2e():
-        if graphed is None:
-            a, b, c = pv_h.to(dev, non_blocking=True), ids_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True)
-            return torch.stack(trainer.train_step(model, opt, a, b, c, alpha)).cpu()
-        return graphed(pv_h, ids_h, mask_h, alpha).cpu()      # pinned host batch -> static device buffers -> replay
+        # strings -> WordPiece ids (pinned) -> H2D -> step (graph replay) -> scheduler cadence -> losses D2H
+        e2e_idx[0] += 1
+        return model.training_step((pv_h, smiles), e2e_idx[0]).cpu()
 
     log("model built; capturing / first step")
     if graphed is not None:
@@ -251,6 +313,7 @@ def run_ours(args):
             if rank == 0:
                 print("graph capture failed (%s: %s); falling back to eager launches" % (type(ex).__name__, ex), file=sys.stderr)
             graphed = None
+            model.use_cuda_graph = False
 
     log("first step done (graph=%s); eager counting step" % (graphed is not None))
     _lib.reset_launch_count()
@@ -295,6 +358,9 @@ def run_ours(args):
     e1.record()
     sync()
     ms_e2e = e0.elapsed_time(e1)
+    model.training_step_outputs.clear()
+    e2e_ids = model.tokenizer(smiles).input_ids[:, 1:]
+    assert e2e_ids.shape[1] == ids_h.shape[1], (e2e_ids.shape, ids_h.shape)   # same padded width as the resident batch
 
     t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -303,7 +369,8 @@ def run_ours(args):
 
     # every rank runs the instrumented step (it contains the step's collectives); rank 0 reports it
     log("timed regions done; instrumented step")
-    roof, extra = kernel_rooflines(torch, kernels, model, step_eager, B, world)
+    roof, extra = kernel_rooflines(torch, kernels, model, step_eager, B, world,
+                                   None if graphed is None else (trainer, opt, pv, ids, mask, alpha))
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -321,7 +388,9 @@ def run_ours(args):
             "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B, world),
             "e2e": {"value": B * world / (ms_e2e / args.steps / 1e3), "unit": "molecules/s",
                     "h2d_bytes_per_step": (pv_h.numel() * 4 + ids_h.numel() * 8 + mask_h.numel() * 8),
-                    "d2h_bytes_per_step": 16},
+                    "d2h_bytes_per_step": 16,
+                    "api": "SPMM.training_step((pv, list of %d SMILES strings), batch_idx): native WordPiece tokeniser, H2D of the "
+                           "pinned batch, CUDA-graph replay, scheduler cadence, losses read back - all inside the timed region" % B},
             "gpu_launches": launches if graphed is None else launches_per_step * args.steps,
             "launch_mode": "eager" if graphed is None else "cuda_graph (one captured graph of the whole step, replayed)",
             "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "losses_last_step": losses,
@@ -329,18 +398,94 @@ def run_ours(args):
             "step_frac_of_bf16_sustained": fl / (ms_step / 1e3) / 1e12 / (pk["bf16_tflops_sustained"] * world),
             "roofline": roof, "roofline_extra": extra, "peaks": pk}
     if world == 1 and not args.no_cpu_baseline:
-        v, ms_cpu, cores = cpu_reference_steps(1, 1, 8, args.seq_len, args.ragged)
+        # free our arm's memory first: the eager baseline keeps ~40 GB of autograd state at B=96
+        if graphed is not None:
+            graphed.graphs.clear()
+        graphed = None
+        model.__dict__.pop("_stepper", None)
+        torch.cuda.empty_cache()
+        try:
+            v, ms_gpu, _ = cpu_reference_steps(3, 2, B, args.seq_len, args.ragged, device=dev)
+            line["gpu_eager_baseline"] = {"value": v, "unit": "molecules/s", "ms_per_step": ms_gpu, "kind": "port",
+                                          "what": "oracle/spmm_ref.py (the reference's algorithm, eager PyTorch) on this GPU under "
+                                                  "torch.autocast(bfloat16): batch %d, same shapes / queue / step body, median of 3 "
+                                                  "CUDA-event-timed steps after 2 warm-ups; cuBLAS / ATen kernels, the reference's 2B "
+                                                  "multinomial().item() syncs included" % B}
+        except Exception as ex:                              # noqa: BLE001
+            line["gpu_eager_baseline"] = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+        torch.cuda.empty_cache()
+        v, ms_cpu, cores = cpu_reference_steps(5, 1, 8, args.seq_len, args.ragged)
         line["cpu_baseline"] = {"value": v, "unit": "molecules/s", "cores": cores, "kind": "port",
-                                "sample": "1 timed step (after 1 warm-up) of batch 8, full queue 36864, fp32 fwd+bwd+clip+AdamW, "
-                                          "oracle/spmm_ref.py on the host cores (%.1f s/step)" % (ms_cpu / 1e3)}
+                                "sample": "median of 5 timed steps (after 1 warm-up) of batch 8, full queue 36864, fp32 "
+                                          "fwd+bwd+clip+AdamW, oracle/spmm_ref.py (port of the reference's algorithm, pinned by golden "
+                                          "vectors) on the host cores (%.1f s/step)" % (ms_cpu / 1e3)}
     print(json.dumps(line), flush=True)
     if world > 1:
         shutdown_distributed(dist, torch, graphed)
 
 
-def kernel_rooflines(torch, kernels, model, step_fn, B, world):
-    """One extra instrumented step: CUDA events (current stream) around every GEMM / EMA / ITC launch."""
+def graph_timed_gemms(torch, kernels, graph_args, model):
+    """Times every GEMM launch INSIDE a replay of the step's CUDA graph: a second graph of the step is captured with the
+    GEMM kernel's %globaltimer phase stamps switched on (each launch gets its own slot of a ring, baked into the graph),
+    replayed, and read back.  Per launch: [first CTA past griddepcontrol.wait (its predecessor has finished), last CTA
+    exit].  The launches run back to back with warm L2 and programmatic dependent launch exactly as in the timed
+    region - what CUDA events around eager launches cannot give.  Returns (ms per step, flops per step, launches, shapes)."""
+    from spmm_b200 import _lib
+    trainer, opt, pv, ids, mask, alpha = graph_args
+    SLOTS = 2048
+    ring = torch.zeros(SLOTS * 148 * 16, dtype=torch.int64, device=pv.device)
+    shapes = []
+    orig = kernels.gemm
+
+    def rec(a, b, M, N, K_, **k):
+        mode = "+".join(n for n, on in (("f32acc", k.get("accumulate")), ("f32", k.get("out_f32") and not k.get("accumulate")),
+                                        ("bias", k.get("bias") is not None), ("gelu", k.get("gelu")),
+                                        ("pre", k.get("pre_act_out") is not None), ("drop", k.get("dropout_p", 0) > 0),
+                                        ("res", k.get("residual") is not None), ("dgelu", k.get("dgelu_pre") is not None),
+                                        ("amn", k.get("a_mn")), ("bmn", k.get("b_mn"))) if on) or "plain"
+        shapes.append((M, N, K_, mode))
+        return orig(a, b, M, N, K_, **k)
+    g2 = trainer.GraphedTrainStep(model, opt, warmup_steps=0)
+    kernels.gemm = rec
+    _lib.lib().spmm_gemm_debug_trace_ring(ring.data_ptr(), SLOTS)
+    try:
+        g2(pv, ids, mask, alpha)                  # capture (records the launch order) + first replay
+    finally:
+        kernels.gemm = orig
+        _lib.lib().spmm_gemm_debug_trace(None)
+    n = len(shapes)
+    if n == 0 or n > SLOTS:
+        return None
+    best = None
+    for _ in range(3):                            # replays: the stamps of the last one are read
+        ring.zero_()
+        g2(pv, ids, mask, alpha)
+        torch.cuda.synchronize()
+        tr = ring.view(SLOTS, 148, 16)[:n].cpu()
+        used = tr[:, :, 1] > 0                    # slot 1 = past the dependency wait, slot 8 = exit (gemm.cu trace_mark)
+        big = torch.iinfo(torch.int64).max
+        start = torch.where(used, tr[:, :, 1], torch.full_like(tr[:, :, 1], big)).min(dim=1).values
+        end = tr[:, :, 8].max(dim=1).values
+        ok = used.any(dim=1)
+        dur_us = ((end - start).double() / 1e3) * ok        # launches on the 1-CTA kernel carry no stamps (tiny problems)
+        tot = float(dur_us.sum()) / 1e3
+        if best is None or tot < best[0]:
+            best = (tot, dur_us.clone(), ok.clone())
+    g2.graphs.clear()
+    fl = sum(2.0 * M * N * K_ for (M, N, K_, _), o in zip(shapes, best[2].tolist()) if o)
+    return best[0], fl, int(best[2].sum()), shapes, best[1]
+
+
+def kernel_rooflines(torch, kernels, model, step_fn, B, world, graph_args=None):
+    """GEMM: in-graph timing (graph_timed_gemms); plus one instrumented eager step with CUDA events (current stream) around
+    every GEMM / EMA / ITC launch (EMA and ITC figures, and the eager GEMM figure kept for comparison)."""
     pk = peaks()
+    in_graph = None
+    if graph_args is not None:
+        try:
+            in_graph = graph_timed_gemms(torch, kernels, graph_args, model)
+        except Exception as ex:                   # noqa: BLE001
+            print("in-graph GEMM timing failed (%s: %s); using the event-timed eager step" % (type(ex).__name__, ex), file=sys.stderr)
     rec = {"gemm": [], "ema": [], "itc": []}
     orig = {"gemm": kernels.gemm, "ema": kernels.ema, "itc": kernels.itc}
 
@@ -398,12 +543,34 @@ def kernel_rooflines(torch, kernels, model, step_fn, B, world):
             for sh, (n_, ms_, w_, kus) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 f.write("M=%6d N=%5d K=%5d %-30s n=%4d  events %8.3f ms avg %6.1f us %6.1f TF/s | in-kernel avg %6.1f us %6.1f TF/s\n"
                         % (sh[0], sh[1], sh[2], sh[3], n_, ms_, 1e3 * ms_ / n_, w_ / ms_ / 1e9, kus / n_, w_ / n_ / max(kus / n_, 1e-9) / 1e6))
-    g_ms, g_fl, g_n = tot["gemm"]
+    ev_ms, ev_fl, ev_n = tot["gemm"]
+    if in_graph is not None:
+        g_ms, g_fl, g_n = in_graph[0], in_graph[1], in_graph[2]
+        how = ("every 2-CTA GEMM launch timed inside a replay of the step's CUDA graph with in-kernel %globaltimer stamps "
+               "(first CTA past its dependency wait -> last CTA exit), summed over the step")
+    else:
+        g_ms, g_fl, g_n = ev_ms, ev_fl, ev_n
+        how = "CUDA events around every GEMM launch of one eager step (GPU parked behind a spin kernel first)"
     ach = g_fl / (g_ms / 1e3) / 1e12
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum summed over the gemm2 launches of one step / launches, from the
+    # committed ncu pass over a whole step (profiles/r2_launches_dram.csv; None until that capture exists)
+    traffic = GEMM_DRAM_BYTES_PER_LAUNCH
     roof = {"kernel": "gemm2_bf16_kernel (tcgen05.mma cta_group::2 + TMA + bulk-store epilogue; all fwd/dgrad/wgrad GEMMs of one step)", "bound": "tensor",
             "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
-            "traffic": None, "launches": g_n, "ms_per_step_in_kernel": g_ms, "flops_per_step": g_fl,
+            "traffic": traffic, "launches": g_n, "ms_per_step_in_kernel": g_ms, "flops_per_step": g_fl, "how": how,
+            "flops_per_launch": g_fl / max(g_n, 1), "avg_launch_us": 1e3 * g_ms / max(g_n, 1),
+            "event_timed_eager": {"achieved": ev_fl / (ev_ms / 1e3) / 1e12, "ms_per_step_in_kernel": ev_ms, "launches": ev_n},
             "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)"}
+    if in_graph is not None and os.environ.get("SPMM_BENCH_GEMM_TABLE"):
+        agg = {}
+        for sh, us, ok in zip(in_graph[3], in_graph[4].tolist(), [True] * len(in_graph[3])):
+            a_ = agg.setdefault(sh, [0, 0.0])
+            a_[0] += 1; a_[1] += us
+        with open(os.environ["SPMM_BENCH_GEMM_TABLE"] + ".graph", "w") as f:
+            for sh, (n_, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                if us > 0:
+                    f.write("M=%6d N=%5d K=%5d %-30s n=%4d  in-graph %8.3f ms avg %6.1f us %7.1f TF/s\n"
+                            % (sh[0], sh[1], sh[2], sh[3], n_, us / 1e3, us / n_, 2.0 * sh[0] * sh[1] * sh[2] * n_ / us / 1e6))
     extra = {}
     # `traffic` = dram__bytes_read.sum + dram__bytes_write.sum per call from the committed ncu --set full captures
     # (profiles/r1_ncu_full_itc_ema_r1.csv for the EMA kernel, profiles/r1_ncu_full_itc_tc.csv for the two ITC scans)
