@@ -48,6 +48,8 @@ typedef struct spmm_gemm_epilogue {
   float alpha;
   float dropout_p;             /* inverted dropout on (acc+bias[,gelu]) before the residual (xbert.py:371,449) */
   unsigned long long dropout_seed;
+  float* colsum;               /* optional [N] fp32: += column sums of the bf16 output C (the bias gradient of the dense that
+                                  produced the tensor C is the gradient of; bf16 outputs of the 2-CTA kernel only) */
 } spmm_gemm_epilogue;
 int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C,
                    int ldc, int M, int N, int K, const spmm_gemm_epilogue* epi, void* stream);
@@ -69,7 +71,10 @@ int spmm_attn_debug_trace(void* buf);   /* debug: 32 x u64 %globaltimer stamps p
 int spmm_attn_bwd(const void* d_o, int lddo, const void* q, int ldq, const void* k, int ldk, const void* v,
                   int ldv, const void* o, int ldo, const float* lse, void* dq, int lddq, void* dk, int lddk,
                   void* dv, int lddv, int batch, int heads, int Tq, int Tk, const int* kv_len, int causal,
-                  float scale, float dropout_p, unsigned long long seed, void* stream);
+                  float scale, float dropout_p, unsigned long long seed, float* dbias_q, float* dbias_k, float* dbias_v,
+                  void* stream);
+/* dbias_q/k/v (optional, all or none; [heads*64] fp32 each): += column sums of dq / dk / dv, i.e. the bias gradients of
+ * the query / key / value projections (autograd of xbert.py:280-298), taken from the tiles the kernel already holds. */
 
 /* ------------------------------------------------------------------ LayerNorm (eps 1e-12; xbert.py:184,366,444,670)
  * y = LN(x) * gamma + beta, optional inverted dropout on y (BertEmbeddings, xbert.py:219).

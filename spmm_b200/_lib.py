@@ -15,7 +15,7 @@ vp, i32, i64, f32, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_ulonglon
 class GemmEpilogue(C.Structure):
     _fields_ = [("bias", vp), ("residual", vp), ("ld_residual", i32), ("pre_act", vp), ("ld_pre_act", i32),
                 ("dgelu_pre_act", vp), ("ld_dgelu_pre_act", i32), ("flags", i32), ("alpha", f32),
-                ("dropout_p", f32), ("dropout_seed", u64)]
+                ("dropout_p", f32), ("dropout_seed", u64), ("colsum", vp)]
 
 
 GEMM_OUT_F32, GEMM_ACCUMULATE, GEMM_GELU, GEMM_DGELU, GEMM_DGELU_STORED = 1, 2, 4, 8, 16
@@ -30,7 +30,7 @@ SIGNATURES = {
     "spmm_attn_debug_trace": (i32, [vp]),
     "spmm_attn_fwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, f32, f32, u64, vp]),
     "spmm_attn_bwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32,
-                            i32, vp, i32, f32, f32, u64, vp]),
+                            i32, vp, i32, f32, f32, u64, vp, vp, vp, vp]),
     "spmm_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, f32, f32, u64, vp]),
     "spmm_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, u64, f32, u64, vp, vp]),
     "spmm_embed_text_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),

@@ -16,7 +16,7 @@ int attn_fwd_tc_launch(const void* q, int ldq, const void* k, int ldk, const voi
 int attn_bwd_tc_launch(const void* d_o, int lddo, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
                        const float* lse, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int batch, int heads,
                        int Tq, int Tk, const int* kv_len, int causal, float scale, uint32_t thresh16, float inv_keep,
-                       unsigned long long seed, cudaStream_t st);
+                       unsigned long long seed, float* dbq, float* dbk, float* dbv, cudaStream_t st);
 
 static inline void attn_drop(float p, uint32_t& th, float& ik) {
   th = p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u;
@@ -47,14 +47,16 @@ extern "C" int spmm_attn_fwd(const void* q, int ldq, const void* k, int ldk, con
 extern "C" int spmm_attn_bwd(const void* d_o, int lddo, const void* q, int ldq, const void* k, int ldk, const void* v,
                              int ldv, const void* o, int ldo, const float* lse, void* dq, int lddq, void* dk, int lddk,
                              void* dv, int lddv, int batch, int heads, int Tq, int Tk, const int* kv_len, int causal,
-                             float scale, float dropout_p, unsigned long long seed, void* stream) {
+                             float scale, float dropout_p, unsigned long long seed, float* dbias_q, float* dbias_k,
+                             float* dbias_v, void* stream) {
   SPMM_ARG(d_o && q && k && v && o && lse && dq && dk && dv);
   SPMM_ARG(batch > 0 && heads > 0 && Tq > 0 && Tk > 0 && Tq <= 128 && Tk <= 128);
   SPMM_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && lddo % 8 == 0 && ldo % 8 == 0 && lddq % 8 == 0 &&
            lddk % 8 == 0 && lddv % 8 == 0);
   SPMM_ARG((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)d_o | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0);
+  SPMM_ARG((dbias_q == nullptr) == (dbias_k == nullptr) && (dbias_q == nullptr) == (dbias_v == nullptr));
   uint32_t th; float ik;
   attn_drop(dropout_p, th, ik);
   return attn_bwd_tc_launch(d_o, lddo, q, ldq, k, ldk, v, ldv, lse, dq, lddq, dk, lddk, dv, lddv, batch, heads, Tq, Tk, kv_len,
-                            causal, scale, th, ik, seed, (cudaStream_t)stream);
+                            causal, scale, th, ik, seed, dbias_q, dbias_k, dbias_v, (cudaStream_t)stream);
 }

@@ -467,6 +467,9 @@ struct AttnBwdArgs {
   float inv_keep;
   const unsigned long long* salt;
   int pair, hp, num_tiles;
+  float* dbq;   // optional [heads*64] fp32 each: += column sums of dQ / dK / dV (bias gradients of the q/k/v projections)
+  float* dbk;
+  float* dbv;
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdArgs a) {
@@ -708,6 +711,24 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
       }
       fence_proxy_async();
       bar_sync_at(1, 512);
+      if (a.dbq != nullptr && sw < 12) {
+        // Bias gradients of the q/k/v projections = column sums of dQ / dK / dV (reference: autograd of nn.Linear,
+        // xbert.py:280-298), taken from the staged bf16 tiles instead of a separate pass over the stored tensors.
+        // Thread = (tensor, 64-row slot, column); rows past the sequence hold zeros (their P / dS rows are zero).
+        const int t = threadIdx.x - 64;
+        const int which = t >> 7, s_ = (t >> 6) & 1, c = t & 63;
+        const int hh = a.pair ? h0 + s_ : h0;
+        if (hh < a.heads) {
+          const uint8_t* base = sPd + which * AT_TILE_BYTES + (s_ * 64) * 128 + (c & 7) * 2;
+          const int u = c >> 3;
+          float acc = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 64; ++rr)
+            acc += bf2f(*reinterpret_cast<const __nv_bfloat16*>(base + rr * 128 + ((u ^ (rr & 7)) << 4)));
+          float* dst = which == 0 ? a.dbq : (which == 1 ? a.dbk : a.dbv);
+          atomicAdd(dst + hh * 64 + c, acc);
+        }
+      }
       if (elected) {
         uint8_t* sdq = sPd;
         uint8_t* sdk = sPd + AT_TILE_BYTES;
@@ -747,7 +768,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
 int attn_bwd_tc_launch(const void* d_o, int lddo, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
                        const float* lse, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int batch, int heads,
                        int Tq, int Tk, const int* kv_len, int causal, float scale, uint32_t thresh16, float inv_keep,
-                       unsigned long long seed, cudaStream_t st) {
+                       unsigned long long seed, float* dbq, float* dbk, float* dbv, cudaStream_t st) {
   AttnBwdMaps maps;
   int rc = attn_make_map(&maps.q, q, (uint64_t)heads * 64, (uint64_t)batch * Tq, ldq);
   if (rc) return rc;
@@ -769,6 +790,7 @@ int attn_bwd_tc_launch(const void* d_o, int lddo, const void* q, int ldq, const 
   a.pair = (Tq <= 64 && Tk <= 64) ? 1 : 0;
   a.hp = (heads + 1) / 2;
   a.num_tiles = a.pair ? batch * a.hp : batch * heads;
+  a.dbq = dbq; a.dbk = dbk; a.dbv = dbv;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);

@@ -222,6 +222,81 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2)
+// Blackwell issues two independent fp32 FMAs per instruction on a 64-bit register pair.  The GEMM epilogues are bound by
+// the issue slots of their few warps (TMEM reads leave room for ~8 warps), so their per-element math runs on pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 splat2(float c) { return pk2(c, c); }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// bf16x2 word -> fp32 pair (lo = element 0): a shift and a mask, no conversion instruction
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t u) {
+  return pk2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
+}
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2(f32x2 v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// gelu(x) = x Phi(x) and gelu'(x) = Phi(x) + x phi(x) for a PAIR of pre-activations, exact-erf form (ACT2FN["gelu"],
+// reference xbert.py:430) through Abramowitz-Stegun 7.1.26 (|err(erf)| <= 1.5e-7): with z = |x|/sqrt2, t = 1/(1 + p z),
+// h = 0.5 erfc(z) = 0.5 t (a1 + t (a2 + ... )) exp(-z^2);  Phi(x) = 0.5 + copysign(0.5 - h, x).
+// 2 MUFU (rcp, ex2) per element + 19 pair-wide issue slots per PAIR (the scalar version cost ~35 per element).
+__device__ __forceinline__ void gelu_and_grad2(f32x2 x, f32x2& act, f32x2& grad) {
+  const f32x2 ax = x & 0x7FFFFFFF7FFFFFFFull;
+  const f32x2 d = fma2(ax, splat2(0.3275911f * 0.70710678118654752f), splat2(1.f));
+  float d0, d1;
+  upk2(d, d0, d1);
+  const f32x2 t = pk2(rcp_approx(d0), rcp_approx(d1));
+  const f32x2 xc = mul2(x, splat2(-0.72134752044448170f));      // -0.5 log2(e) x
+  const f32x2 y = mul2(xc, x);                                    // -x^2/2 in log2 units
+  float y0, y1;
+  upk2(y, y0, y1);
+  const f32x2 e = pk2(ex2_approx(y0), ex2_approx(y1));            // exp(-x^2/2)
+  f32x2 pl = fma2(t, splat2(0.5f * 1.061405429f), splat2(0.5f * -1.453152027f));
+  pl = fma2(pl, t, splat2(0.5f * 1.421413741f));
+  pl = fma2(pl, t, splat2(0.5f * -0.284496736f));
+  pl = fma2(pl, t, splat2(0.5f * 0.254829592f));
+  const f32x2 h = mul2(mul2(pl, t), e);                           // 0.5 erfc(|x|/sqrt2) in [0, 0.5]
+  f32x2 q = fma2(h, splat2(-1.f), splat2(0.5f));                  // 0.5 - h >= 0
+  q |= x & 0x8000000080000000ull;                                 // copysign(0.5 - h, x)
+  const f32x2 cdf = add2(q, splat2(0.5f));
+  act = mul2(x, cdf);
+  // x phi(x) = x exp(-x^2/2) / sqrt(2 pi) = (xc e) * (1/sqrt(2 pi)) / (-0.5 log2 e)
+  grad = fma2(mul2(xc, e), splat2(0.3989422804014327f / -0.72134752044448170f), cdf);
+}
+
 // Counter-based RNG for dropout: one 32-bit draw per (seed, stream, index).  splitmix-style finaliser.
 __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
   uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);

@@ -33,6 +33,7 @@ struct GemmParams {
   void* C;
   int ldc;
   const float* bias;
+  float* colsum;   // optional [N] fp32: += column sums of the (bf16-rounded) output (bias gradient of the consumer dense)
   const __nv_bfloat16* residual;
   int ldr;
   __nv_bfloat16* pre;
@@ -450,14 +451,14 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // remote a
 }
 
 struct Gemm2Maps {
-  CUtensorMap a, b, c, side, pre;   // side: residual or dGELU pre-activation (bf16, same shape as C); pre: 2nd output
+  CUtensorMap a, b, c, pre;   // pre: 2nd bf16 output (pre-activation, or gelu' of it)
 };
 
 // One 32-column chunk of this thread's row: fused math on v[32], side operand / result through the staging tile.
 // Staging address of 16-byte unit u of row r in a box: box + r*128 + ((u ^ (r & 7)) << 4).
 __device__ __forceinline__ void epi2_chunk(const GemmParams& p, float (&v)[32], const float* s_bias_chunk, const int row_g,
                                            const int col0, const uint32_t drop_key, uint8_t* out_row, uint8_t* pre_row,
-                                           const int u0, const int sw, const bool has_side) {
+                                           const int u0, const int sw, const bool has_side, const uint4 (&side)[4]) {
   const bool out_f32 = p.flags & SPMM_GEMM_OUT_F32;
   if (p.bias != nullptr) {
 #pragma unroll
@@ -500,11 +501,11 @@ __device__ __forceinline__ void epi2_chunk(const GemmParams& p, float (&v)[32], 
       drop_pair(drop_key, e, p.drop_thresh16, p.drop_inv_keep, v[j], v[j + 1]);
     }
   }
-  if (has_side) {   // bf16 side operand sits where the result goes
+  if (has_side) {   // bf16 side operand (residual / dGELU factor), prefetched from global memory into registers
     const bool do_dgelu = p.flags & SPMM_GEMM_DGELU, stored = p.flags & SPMM_GEMM_DGELU_STORED;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint4 sv = *reinterpret_cast<const uint4*>(out_row + (((u0 + i) ^ sw) << 4));
+      const uint4 sv = side[i];
       float s[8];
       unpack_bf16x2(sv.x, s[0], s[1]); unpack_bf16x2(sv.y, s[2], s[3]);
       unpack_bf16x2(sv.z, s[4], s[5]); unpack_bf16x2(sv.w, s[6], s[7]);
@@ -532,6 +533,75 @@ __device__ __forceinline__ void epi2_chunk(const GemmParams& p, float (&v)[32], 
   }
 }
 
+// ---- fast epilogue paths on packed fp32 pairs (FFMA2): the three shapes that carry the step ------------------------
+enum { EPI_GENERIC = 0, EPI_GELU_GRAD = 1, EPI_DGELU_MUL = 2, EPI_LINEAR = 3 };
+
+__device__ __forceinline__ void stage_units(uint8_t* row, const int u0, const int sw, const f32x2 (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 o;
+    o.x = f32x2_to_bf16x2(v[4 * i]); o.y = f32x2_to_bf16x2(v[4 * i + 1]);
+    o.z = f32x2_to_bf16x2(v[4 * i + 2]); o.w = f32x2_to_bf16x2(v[4 * i + 3]);
+    *reinterpret_cast<uint4*>(row + (((u0 + i) ^ sw) << 4)) = o;
+  }
+}
+__device__ __forceinline__ void add_bias2(f32x2 (&v)[16], const float* s_bias_chunk) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(s_bias_chunk + 4 * i);   // smem broadcast, two pairs
+    v[2 * i] = add2(v[2 * i], b.x);
+    v[2 * i + 1] = add2(v[2 * i + 1], b.y);
+  }
+}
+// FFN-up forward (reference xbert.py:434-437): act = gelu(acc + bias) -> out box, gelu'(acc + bias) -> 2nd output box
+__device__ __forceinline__ void epi2_gelu_grad(f32x2 (&v)[16], const float* s_bias_chunk, uint8_t* out_row, uint8_t* pre_row,
+                                               const int u0, const int sw) {
+  add_bias2(v, s_bias_chunk);
+  f32x2 gr[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) gelu_and_grad2(v[j], v[j], gr[j]);
+  stage_units(pre_row, u0, sw, gr);
+  stage_units(out_row, u0, sw, v);
+}
+// FFN backward: d pre = (dY . W2) * gelu'(pre), the factor stored by the forward
+__device__ __forceinline__ void epi2_dgelu_mul(f32x2 (&v)[16], const uint4 (&side)[4], uint8_t* out_row, const int u0,
+                                               const int sw) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[4 * i] = mul2(v[4 * i], bf16x2_to_f32x2(side[i].x));
+    v[4 * i + 1] = mul2(v[4 * i + 1], bf16x2_to_f32x2(side[i].y));
+    v[4 * i + 2] = mul2(v[4 * i + 2], bf16x2_to_f32x2(side[i].z));
+    v[4 * i + 3] = mul2(v[4 * i + 3], bf16x2_to_f32x2(side[i].w));
+  }
+  stage_units(out_row, u0, sw, v);
+}
+// dense (+ bias) (+ inverted dropout) (+ residual): BertSelfOutput / BertOutput (xbert.py:369-373, 447-451), QKV, dgrads
+__device__ __forceinline__ void epi2_linear(const GemmParams& p, f32x2 (&v)[16], const float* s_bias_chunk, const int row_g,
+                                            const int col0, const uint32_t drop_key, const bool has_res,
+                                            const uint4 (&side)[4], uint8_t* out_row, const int u0, const int sw) {
+  if (p.bias != nullptr) add_bias2(v, s_bias_chunk);
+  if (p.drop_thresh16 != 0) {
+    const uint32_t e0 = (uint32_t)row_g * (uint32_t)p.N + (uint32_t)col0;   // even (N % 8 == 0, col0 % 32 == 0)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t hbits = drop_bits2(drop_key, e0 + 2 * j);
+      const float m0 = ((hbits & 0xFFFFu) >= p.drop_thresh16) ? p.drop_inv_keep : 0.f;
+      const float m1 = ((hbits >> 16) >= p.drop_thresh16) ? p.drop_inv_keep : 0.f;
+      v[j] = mul2(v[j], pk2(m0, m1));
+    }
+  }
+  if (has_res) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[4 * i] = add2(v[4 * i], bf16x2_to_f32x2(side[i].x));
+      v[4 * i + 1] = add2(v[4 * i + 1], bf16x2_to_f32x2(side[i].y));
+      v[4 * i + 2] = add2(v[4 * i + 2], bf16x2_to_f32x2(side[i].z));
+      v[4 * i + 3] = add2(v[4 * i + 3], bf16x2_to_f32x2(side[i].w));
+    }
+  }
+  stage_units(out_row, u0, sw, v);
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -541,9 +611,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
   uint64_t* empty_bar = full_bar + kStages2;
   uint64_t* tfull_bar = empty_bar + kStages2;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* side_full = tempty_bar + 2;     // side operand of the current tile landed in the staging tile
-  uint64_t* stage_free = side_full + 1;     // both halves' stores of the previous tile have read the staging tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(staging + STG_BYTES + 512);
 
   pdl_trigger();
@@ -564,7 +632,6 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
     tma_prefetch_desc(&maps.a);
     tma_prefetch_desc(&maps.b);
     tma_prefetch_desc(&maps.c);
-    if (has_side) tma_prefetch_desc(&maps.side);
     if (has_pre) tma_prefetch_desc(&maps.pre);
   }
   if (warp == 1 && lane == 0) {
@@ -576,8 +643,6 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       mbar_init(&tfull_bar[s], 1);    // multicast commit
       mbar_init(&tempty_bar[s], 16);  // leader's copy: 8 epilogue warps x 2 CTAs
     }
-    mbar_init(side_full, 1);
-    mbar_init(stage_free, 2);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -665,22 +730,6 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp == 3 && lane == 0 && has_side) {
-    // ===================== side-operand loader (both CTAs: own 128 rows) =====================
-    uint32_t ph = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int mn = tile % num_mn;
-      const int m0 = (mn % num_m) * 2 * BM + (int)rank * BM, n0 = (mn / num_m) * BN2;
-      mbar_wait(stage_free, ph ^ 1);   // previous tile's stores have drained the staging tile
-      int nbox = 0;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) nbox += (n0 + 64 * b < p.N) ? 1 : 0;
-      mbar_expect_tx(side_full, nbox * STG_BOX_BYTES);
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (n0 + 64 * b < p.N) tma_load_2d(staging + b * STG_BOX_BYTES, &maps.side, side_full, n0 + 64 * b, m0);
-      ph ^= 1;
-    }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs: own 128 rows x 256 columns) =====================
     const int q = warp & 3;             // TMEM lane quadrant this warp may read
@@ -692,12 +741,37 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
     const uint32_t drop_key = p.drop_thresh16 ? fold_seed(salted(p.drop_seed, p.salt)) : 0u;
     // 64-column sub-phases when a chunk needs two boxes' worth of staging (f32 output, or a 2nd bf16 output)
     const int nsub = (out_f32 || has_pre) ? 2 : 1;
+    // fast path selection (warp-uniform, once per kernel): packed-pair math for the shapes that carry the step
+    int mode = EPI_GENERIC;
+    if (p.alpha == 1.f && !out_f32) {
+      const bool g = p.flags & SPMM_GEMM_GELU, dg = p.flags & SPMM_GEMM_DGELU, st = p.flags & SPMM_GEMM_DGELU_STORED;
+      if (g && st && has_pre && !has_side && p.drop_thresh16 == 0 && p.bias != nullptr) mode = EPI_GELU_GRAD;
+      else if (dg && st && !g && !has_pre && p.bias == nullptr && p.drop_thresh16 == 0) mode = EPI_DGELU_MUL;
+      else if (!g && !dg && !has_pre) mode = EPI_LINEAR;
+    }
+    // The bf16 side operand (residual, or the stored gelu' factor) is read straight from global memory by the thread
+    // that owns the row, one 32-column chunk (64 B) ahead of its use.  It used to arrive by TMA in the output staging
+    // tile, which chained side load -> math -> store drain -> next side load per tile (8 us per tile on the dGELU GEMM
+    // against 5.3 us of mainloop); register prefetch has no such chain and starts before the accumulator is complete.
+    const __nv_bfloat16* side = (p.flags & SPMM_GEMM_DGELU) ? p.aux : p.residual;
+    const int lds = (p.flags & SPMM_GEMM_DGELU) ? p.ldaux : p.ldr;
     int acc = 0;
-    uint32_t acc_phase = 0, side_phase = 0;
+    uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int mn = tile % num_mn;
       const int m0 = (mn % num_m) * 2 * BM + (int)rank * BM, n0 = (mn / num_m) * BN2;
       const int nh0 = n0 + 128 * h;     // first column of this half
+      const bool row_ok = m0 + r < p.M;
+      const __nv_bfloat16* side_row = has_side ? side + (size_t)(m0 + r) * lds : nullptr;
+      uint4 side_next[4];
+      auto load_side = [&](int col, uint4(&dst)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (has_side && row_ok && col + 8 * i + 8 <= p.N) dst[i] = __ldg(reinterpret_cast<const uint4*>(side_row + col + 8 * i));
+          else dst[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      load_side(nh0, side_next);        // in flight while the MMAs of this tile are still running
       // staging boxes of this half are free (previous stores have read them) and the previous bias reads are done
       if (elected) bulk_wait_read0();
       bar_sync_named(bar_id, 128);
@@ -707,7 +781,6 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
         bar_sync_named(bar_id, 128);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
-      if (has_side) mbar_wait(side_full, side_phase);
       tc_fence_after();
       if (warp == 4 && lane == 0 && tile == pair) trace_mark(p, 5);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN2 + 128 * h;
@@ -725,11 +798,11 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
           const int c = sub * nchunk + cc;            // chunk within the half: columns nh0 + 32c
           const int col0 = nh0 + 32 * c;
           if (col0 >= p.N) break;                     // warp-uniform
-          tmem_ld_wait();
-          float v[32];
+          uint4 side_cur[4];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
-          if (cc + 1 < nchunk && col0 + 32 < p.N) tmem_ld32(taddr + (c + 1) * 32, rr);
+          for (int i = 0; i < 4; ++i) side_cur[i] = side_next[i];
+          if (c + 1 < 4) load_side(col0 + 32, side_next);
+          tmem_ld_wait();
           // staging placement: bf16 -> box 2h + (c >> 1), units 4*(c & 1)..+3; pre mode -> act box 2h+1 / pre box 2h,
           // units 4*cc..+3; f32 -> box 2h + cc, units 0..7
           uint8_t* out_row;
@@ -741,7 +814,22 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
             pre_row = staging + (2 * h) * STG_BOX_BYTES + r * 128;
             u0 = 4 * cc;
           } else { out_row = staging + (2 * h + (c >> 1)) * STG_BOX_BYTES + r * 128; u0 = 4 * (c & 1); }
-          epi2_chunk(p, v, s_bias + 128 * h + 32 * c, m0 + r, col0, drop_key, out_row, pre_row, u0, sw, has_side);
+          const bool more = cc + 1 < nchunk && col0 + 32 < p.N;
+          if (mode != EPI_GENERIC) {
+            f32x2 v2[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v2[j] = pk2(__uint_as_float(rr[2 * j]), __uint_as_float(rr[2 * j + 1]));
+            if (more) tmem_ld32(taddr + (c + 1) * 32, rr);
+            if (mode == EPI_GELU_GRAD) epi2_gelu_grad(v2, s_bias + 128 * h + 32 * c, out_row, pre_row, u0, sw);
+            else if (mode == EPI_DGELU_MUL) epi2_dgelu_mul(v2, side_cur, out_row, u0, sw);
+            else epi2_linear(p, v2, s_bias + 128 * h + 32 * c, m0 + r, col0, drop_key, has_side, side_cur, out_row, u0, sw);
+          } else {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
+            if (more) tmem_ld32(taddr + (c + 1) * 32, rr);
+            epi2_chunk(p, v, s_bias + 128 * h + 32 * c, m0 + r, col0, drop_key, out_row, pre_row, u0, sw, has_side, side_cur);
+          }
         }
         if (sub == nsub - 1) {            // accumulator fully read: hand the TMEM buffer back to the MMA issuer
           tc_fence_before();
@@ -752,6 +840,29 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
         fence_proxy_async();
         bar_sync_named(bar_id, 128);
         if (warp == 4 && lane == 0 && tile == pair && sub == 0) trace_mark(p, 13);
+        if (p.colsum != nullptr && !out_f32 && !has_pre) {
+          // Column sums of this CTA's 128 x 128 half-tile from the staged bf16 values (what a separate pass over the
+          // stored tensor would read): thread = (column pair, row half), 64 rows each; rows >= M are skipped.
+          const int t = threadIdx.x - 128 - 128 * h;
+          const int cp = t & 63, rh = t >> 6;                  // columns nh0 + 2cp, +1; rows 64rh .. 64rh + 63
+          const uint8_t* box = staging + (2 * h + (cp >> 5)) * STG_BOX_BYTES;
+          const int u = (cp & 31) >> 2, off = (cp & 3) * 4;     // 16-byte unit and byte offset of the column pair
+          f32x2 acc2 = 0ull;
+          const int rmax = min(64, p.M - (m0 + 64 * rh));      // rows of this CTA's tile that exist
+#pragma unroll 8
+          for (int i = 0; i < 64; ++i) {
+            const int rr_ = 64 * rh + i;
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(box + rr_ * 128 + ((u ^ (rr_ & 7)) << 4) + off);
+            if (i < rmax) acc2 = add2(acc2, bf16x2_to_f32x2(w));
+          }
+          float s0, s1;
+          upk2(acc2, s0, s1);
+          const int col = nh0 + 2 * cp;
+          if (col < p.N) {
+            atomicAdd(p.colsum + col, s0);
+            atomicAdd(p.colsum + col + 1, s1);
+          }
+        }
         if (elected) {
           const int cs = nh0 + sub * 64;   // first column of this sub-phase (nsub == 2)
           if (out_f32) {
@@ -776,12 +887,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
           bulk_commit();
         }
       }
-      if (has_side && elected) {   // let the side loader refill the staging tile for the next tile
-        bulk_wait_read0();
-        mbar_arrive(stage_free);
-      }
       if (warp == 4 && lane == 0) trace_mark(p, tile == pair ? 6 : 10);
-      side_phase ^= 1;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -931,6 +1037,7 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   if (g_trace && g_trace_slots > 0) p.trace = g_trace + (size_t)(g_trace_next++ % g_trace_slots) * kNumSMs * 16;
   if (epi) {
     p.bias = epi->bias;
+    p.colsum = epi->colsum;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(epi->residual); p.ldr = epi->ld_residual;
     p.pre = reinterpret_cast<__nv_bfloat16*>(epi->pre_act); p.ldp = epi->ld_pre_act;
     p.aux = reinterpret_cast<const __nv_bfloat16*>(epi->dgelu_pre_act); p.ldaux = epi->ld_dgelu_pre_act;
@@ -955,11 +1062,16 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   SPMM_ARG(!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
   SPMM_ARG(!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
   SPMM_ARG(!p.pre || (reinterpret_cast<uintptr_t>(p.pre) & 15) == 0);
-  // 2-CTA 256x256 pair tiles; its staged epilogue has one staging tile, so a side operand excludes f32 / 2nd outputs
-  // (bulk tensor stores were observed to touch the rest of a partially covered 16-byte unit past N, so the 1-CTA
-  // kernel with element-granular stores keeps the ragged-N problems, e.g. the 300-column LM head)
-  const bool use2 = g_use_2cta && !g_force_bn && M > BM && N > 128 && !(has_side && (out_f32 || p.pre)) &&
+  // 2-CTA 256x256 pair tiles (bulk tensor stores were observed to touch the rest of a partially covered 16-byte unit
+  // past N, so the 1-CTA kernel with element-granular stores keeps the ragged-N problems, e.g. the 300-column LM head;
+  // a side operand with an f32 output is not a shape the step has - the generic 1-CTA path keeps it)
+  const bool use2 = g_use_2cta && !g_force_bn && M > BM && N > 128 && !(has_side && out_f32) &&
                     N % (out_f32 ? 8 : 16) == 0;
+  // column sums ride on the staged bf16 epilogue of the 2-CTA kernel; small / ragged problems on the 1-CTA kernel get
+  // the same result from a separate pass over the bf16 output
+  SPMM_ARG(!p.colsum || !out_f32);
+  float* colsum_after = nullptr;
+  if (p.colsum && !(use2 && !p.pre)) { colsum_after = p.colsum; p.colsum = nullptr; }
   const int bn = use2 ? BN2 : pick_bn(M, N);
   const int slots = use2 ? kNumSMs / 2 : kNumSMs;
   const int tiles_mn = use2 ? ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2) : ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
@@ -995,17 +1107,18 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
     // epilogue staging boxes: [128 rows][128 bytes] = 64 bf16 or 32 f32 columns
     rc = make_map(&maps.c, C, N, M, ldc, out_f32 ? 32 : 64, BM, out_f32);
     if (rc) return rc;
-    maps.side = maps.c;
     maps.pre = maps.c;
-    if (has_side) {
-      rc = p.aux ? make_map(&maps.side, p.aux, N, M, p.ldaux, 64, BM) : make_map(&maps.side, p.residual, N, M, p.ldr, 64, BM);
-      if (rc) return rc;
-    }
     if (p.pre) {
       rc = make_map(&maps.pre, p.pre, N, M, p.ldp, 64, BM);
       if (rc) return rc;
     }
-    return launch2(maps, p, st);
+    rc = launch2(maps, p, st);
+  } else {
+    rc = bn == 256 ? launch<256>(ma, mb, p, st) : launch<128>(ma, mb, p, st);
   }
-  return bn == 256 ? launch<256>(ma, mb, p, st) : launch<128>(ma, mb, p, st);
+  if (rc == 0 && colsum_after != nullptr) {
+    SPMM_ARG(N % 8 == 0);
+    rc = spmm_colsum_bf16(C, ldc, colsum_after, M, N, stream);
+  }
+  return rc;
 }

@@ -29,8 +29,9 @@ def _chk_cuda(*ts):
 
 def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, out=None, out_f32=False, accumulate=False, bias=None,
          residual=None, pre_act_out=None, dgelu_pre=None, gelu=False, dropout_p=0.0, seed=0, ldc=None,
-         dgelu_stored=False):
-    """C[M,N] (+)= epi(A.B^T).  a: [M,K] (K-major) or [K,M] (a_mn); b: [N,K] or [K,N] (b_mn); row stride = ld."""
+         dgelu_stored=False, colsum_out=None):
+    """C[M,N] (+)= epi(A.B^T).  a: [M,K] (K-major) or [K,M] (a_mn); b: [N,K] or [K,N] (b_mn); row stride = ld.
+    `colsum_out` [N] fp32 += column sums of the bf16 result (bias gradient fused into the producing GEMM)."""
     _chk_cuda(a, b)
     assert a.dtype == BF16 and b.dtype == BF16 and a.stride(-1) == 1 and b.stride(-1) == 1
     if out is None:
@@ -41,7 +42,7 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, out=None, out_f32=False, accu
     epi = GemmEpilogue(_p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
                        _p(pre_act_out), pre_act_out.stride(0) if pre_act_out is not None else 0,
                        _p(dgelu_pre), dgelu_pre.stride(0) if dgelu_pre is not None else 0,
-                       flags, 1.0, float(dropout_p), int(seed))
+                       flags, 1.0, float(dropout_p), int(seed), _p(colsum_out))
     call("spmm_gemm_bf16", a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
          out.data_ptr(), out.stride(0) if ldc is None else ldc, M, N, K, C.byref(epi), _st())
     return out
@@ -54,11 +55,14 @@ def attn_fwd(q, k, v, out, lse, batch, heads, Tq, Tk, kv_len, causal, scale, dro
     return out
 
 
-def attn_bwd(do, q, k, v, o, lse, dq, dk, dv, batch, heads, Tq, Tk, kv_len, causal, scale, dropout_p=0.0, seed=0):
+def attn_bwd(do, q, k, v, o, lse, dq, dk, dv, batch, heads, Tq, Tk, kv_len, causal, scale, dropout_p=0.0, seed=0,
+             dbias=None):
+    """`dbias` = (dbq, dbk, dbv) fp32 [heads*64] views: += column sums of dq / dk / dv (projection bias gradients)."""
+    dbq, dbk, dbv = dbias if dbias is not None else (None, None, None)
     call("spmm_attn_bwd", do.data_ptr(), do.stride(0), q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
          v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0), lse.data_ptr(), dq.data_ptr(), dq.stride(0),
          dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0), batch, heads, Tq, Tk, _p(kv_len), int(causal),
-         float(scale), float(dropout_p), int(seed), _st())
+         float(scale), float(dropout_p), int(seed), _p(dbq), _p(dbk), _p(dbv), _st())
 
 
 def layernorm_fwd(x, gamma, beta, eps, save_stats=True, dropout_p=0.0, seed=0):

@@ -125,9 +125,10 @@ class _AttnBlock(torch.autograd.Function):
         if enc is None:
             q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
             dqkv = torch.empty_like(qkv)
+            gb = W.g_bqkv                                 # [q.b | k.b | v.b] gradients: summed inside the attention kernel
             K.attn_bwd(do, q, k, v, o, lse, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], g.B, W.heads, g.Tq, g.Tk,
-                       g.kv_len, g.causal, scale, p_attn, seed_a)
-            K.colsum(dqkv, W.g_bqkv)
+                       g.kv_len, g.causal, scale, p_attn, seed_a,
+                       dbias=None if gb is None else (gb[:H], gb[H:2 * H], gb[2 * H:]))
             _wgrad(dqkv, x, W.g_wqkv, 3 * H, H, M)
             dx = K.gemm(dqkv, W.wqkv, M, H, 3 * H, b_mn=True, residual=dxs)
             return dx, None, None, None, None, None, None
@@ -136,11 +137,10 @@ class _AttnBlock(torch.autograd.Function):
         dq = torch.empty_like(qkv)
         dkv = torch.empty_like(kvbuf)
         K.attn_bwd(do, qkv, k, v, o, lse, dq, dkv[:, :H], dkv[:, H:], g.B, W.heads, g.Tq, g.Tk, g.kv_len, g.causal,
-                   scale, p_attn, seed_a)
-        K.colsum(dq, W.g_bq)
+                   scale, p_attn, seed_a,
+                   dbias=None if W.g_bq is None else (W.g_bq, W.g_bkv[:H], W.g_bkv[H:]))
         _wgrad(dq, x, W.g_wq, H, H, M)
         dx = K.gemm(dq, W.wq, M, H, H, b_mn=True, residual=dxs)
-        K.colsum(dkv, W.g_bkv)
         _wgrad(dkv, enc, W.g_wkv, 2 * H, H, Mk)
         denc = K.gemm(dkv, W.wkv, Mk, H, 2 * H, b_mn=True) if ctx.needs_input_grad[1] else None
         return dx, denc, None, None, None, None, None
@@ -182,8 +182,8 @@ class _FfnBlock(torch.autograd.Function):
         dxs, dxb = K.layernorm_bwd(dy.contiguous(), xsum, mean, rstd, W.ln_g, W.g_ln_g, W.g_ln_b, dbias=W.g_b2,
                                    want_branch=True, branch_dropout_p=p_hid, branch_seed=seed_h)
         _wgrad(dxb, act, W.g_w2, H, I, M)
-        dpre = K.gemm(dxb, W.w2, M, I, H, b_mn=True, dgelu_pre=pre, dgelu_stored=_DGELU_STORED)   # (dxb . W2) * gelu'(pre)
-        K.colsum(dpre, W.g_b1)
+        # (dxb . W2) * gelu'(pre); the intermediate bias gradient (column sums of dpre) rides on the same epilogue
+        dpre = K.gemm(dxb, W.w2, M, I, H, b_mn=True, dgelu_pre=pre, dgelu_stored=_DGELU_STORED, colsum_out=W.g_b1)
         _wgrad(dpre, x, W.g_w1, I, H, M)
         dx = K.gemm(dpre, W.w1, M, H, I, b_mn=True, residual=dxs)
         return dx, None, None, None

@@ -193,6 +193,29 @@ def test_gemm_epilogues_multi_tile(M, N, K_):
     assert rel_err(acc, want) < 1e-3
 
 
+@pytest.mark.parametrize("M,N,K_,mode", [(6144, 3072, 768, "dgelu"), (5184, 768, 768, "linear"), (300, 3072, 256, "dgelu"),
+                                           (96, 128, 64, "small")])
+def test_gemm_fused_column_sums(M, N, K_, mode):
+    """`colsum_out` += column sums of the bf16 output, taken from the epilogue's staging tile (bias gradient of
+    BertIntermediate fused into the dGELU dgrad GEMM, autograd of xbert.py:434-437); accumulates across calls; problems
+    on the 1-CTA kernel get the same numbers from a separate pass."""
+    a = rnd(M, K_, scale=0.5, dtype=BF, seed=1)
+    b = rnd(K_, N, scale=0.05, dtype=BF, seed=2)            # [K, N]: b_mn like a dgrad
+    cs = torch.full((N,), 3.0, device=DEV)
+    kw = {}
+    if mode == "dgelu":
+        kw = dict(dgelu_pre=rnd(M, N, dtype=BF, seed=3), dgelu_stored=True)
+    out = K.gemm(a, b, M, N, K_, b_mn=True, colsum_out=cs, **kw)
+    ref = a.float() @ b.float()
+    if mode == "dgelu":
+        ref = ref * kw["dgelu_pre"].float()
+    assert rel_err(out, ref) < 1e-2
+    want = 3.0 + out.float().sum(0)
+    assert float((cs - want).abs().max()) <= 1e-3 * float(want.abs().max()) + 1e-3, float((cs - want).abs().max())
+    out2 = K.gemm(a, b, M, N, K_, b_mn=True, **kw)          # without the option: same product
+    assert torch.equal(out, out2)
+
+
 def test_gemm_wgrad_split_k():
     """dW += dY^T X with both operands MN-major and a long K: split-K partials meet in the f32 reduce-add epilogue."""
     for (n_out, k_in, tokens) in [(768, 768, 6144), (2304, 768, 5184), (768, 3072, 6144)]:
@@ -301,7 +324,12 @@ def test_attention_fwd_bwd(B, h, Tq, Tk, causal, ragged):
         dq = torch.zeros(B * Tq, H, device=DEV, dtype=BF)
         dkv = torch.zeros(B * Tk, 2 * H, device=DEV, dtype=BF)
         dk, dv = dkv[:, :H], dkv[:, H:]
-    K.attn_bwd(do, q, k, v, o, lse, dq, dk, dv, B, h, Tq, Tk, kv_len, causal, 0.125)
+    dbias = torch.zeros(3, H, device=DEV)
+    K.attn_bwd(do, q, k, v, o, lse, dq, dk, dv, B, h, Tq, Tk, kv_len, causal, 0.125, dbias=(dbias[0], dbias[1], dbias[2]))
+    # projection bias gradients = column sums of the bf16 tiles the kernel stored (fused; no separate colsum pass)
+    for name, got, t in (("dbq", dbias[0], dq), ("dbk", dbias[1], dk), ("dbv", dbias[2], dv)):
+        want = t.float().sum(0)
+        assert float((got - want).abs().max()) <= 2e-3 * float(want.abs().max()) + 1e-4, (name, float((got - want).abs().max()))
 
     def flat(t, T):
         return t.permute(0, 2, 1, 3).reshape(B * T, H)
