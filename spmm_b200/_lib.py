@@ -100,8 +100,15 @@ def launch_count():
     return _launches
 
 
+# Measurement aid (tools/skip_table.sh): SPMM_DEBUG_SKIP="spmm_layernorm_fwd,spmm_colsum_bf16" makes the named entry points
+# no-ops, so the step time WITHOUT a kernel family can be read from `bench.py --profile` (results are garbage, timing only).
+_SKIP = frozenset(x for x in os.environ.get("SPMM_DEBUG_SKIP", "").split(",") if x)
+
+
 def call(name, *args):
     global _launches
+    if _SKIP and name in _SKIP:
+        return 0
     _launches += KERNELS_PER_CALL.get(name, 1)
     rc = getattr(lib(), name)(*args)
     if rc != 0:

@@ -16,3 +16,15 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def repo_root():
     return REPO
+
+
+@pytest.fixture(autouse=True)
+def _reset_step_rng_salt(request):
+    """The dropout / sampler kernels add a device "salt" to their seeds (ops.StepRng; training steps advance it).  Kernel
+    tests compare against CPU replicas that assume salt 0, so every GPU test starts from a zero salt whatever ran before."""
+    if request.node.get_closest_marker("gpu") is not None:
+        import torch
+        if torch.cuda.is_available():
+            from spmm_b200 import ops
+            ops.step_rng("cuda").reset(0)
+    yield

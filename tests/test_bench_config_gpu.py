@@ -102,9 +102,9 @@ def test_graphed_training_step_on_bucketed_lengths_equals_eager_step():
     tj, pj = os.path.join(CFG, "config_bert.json"), os.path.join(CFG, "config_bert_property.json")
     Bs = 8
     batches = []
-    for seed, L in ((5, 59), (6, 62)):
-        pv, ids, mask, _ = synth.synthetic_batch(Bs, seed=seed, min_len=20, max_len=L + 1)
-        assert ids.shape[1] <= 64
+    for seed, lo, hi in ((5, 57, 60), (6, 61, 64)):           # widths 57..59 and 61..63: both in the (56, 64] bucket
+        pv, ids, mask, _ = synth.synthetic_batch(Bs, seed=seed, min_len=lo, max_len=hi)
+        assert 56 < ids.shape[1] <= 64
         batches.append((pv.to(DEV), ids.to(DEV), mask.to(DEV)))
     mpm = (torch.rand(Bs, 53, generator=torch.Generator().manual_seed(3)) < 0.5).float().to(DEV)
     out = {}
