@@ -175,6 +175,35 @@ int spmm_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq,
                     float grad_scale, const float* skip_flag, const float* hyper_dev, void* stream);
 /* hyper_dev (device float[3] = lr, 1-beta1^t, sqrt(1-beta2^t)) overrides lr/step when non-NULL (graph replay). */
 
+/* ------------------------------------------------------------------ single-token decode (PV -> SMILES beam search)
+ * Replaces the per-token full-prefix re-run of d_pv2smiles_single.py:26-36 / d_pv2smiles_batched.py:24-59: the stack is
+ * causal, so keys / values of earlier positions are cached.  `t_dev` (device int) = position of the token being fed;
+ * every per-step scalar is read from device memory so one CUDA graph replays for all steps.
+ *   decode_embed:      x[r] = word[ids[r]] + type0 + pos[*t_dev]   (bf16 pre-LayerNorm sum, xbert.py:193-217)
+ *   decode_attn_self:  appends k_new/v_new (bf16 [rows][ldkv]) to cache_k/cache_v (bf16 [tmax][rows][heads*64]) at
+ *                      position t, then softmax(q K^T scale) V over positions 0..t of the row's own beam: position j < t
+ *                      lives in physical row anc[r][j] (beam re-ranking never moves cache data); keys with
+ *                      tokens[r][j] == 0 are masked (text_atts = where(text == 0, 0, 1), d_pv2smiles_single.py:27)
+ *   decode_attn_cross: q against rows (r / group) * Tk .. + Tk of k / v (bf16 [groups*Tk][ldkv]): the property tokens
+ *                      of the row's molecule, projected once and shared by its `group` beams
+ *   beam_step:         per molecule (k beams = rows m*k ..): softmax + top-k of each beam's logits, candidates
+ *                      score + log p; from the 2nd expansion on a candidate ending in sep_id moves to the finished
+ *                      list (score, tokens) and is masked with -1e5, the molecule is done once >= k are finished;
+ *                      otherwise top-k of the k*k candidates become the new beams (tokens, ancestor rows, scores,
+ *                      next_ids rewritten in place); finally *t_dev += 1.  fin_cap >= k*k + k.  trace_* optional
+ *                      [steps][n_mol*k][k] record of each beam's top-k (log p, token).  ticket: zeroed uint32. */
+int spmm_decode_embed(const int64_t* ids, const int* t_dev, const float* word, const float* pos, const float* type0,
+                      void* x, int rows, int H, void* stream);
+int spmm_decode_attn_self(const void* q, int ldq, const void* k_new, const void* v_new, int ldkv, void* cache_k,
+                          void* cache_v, const int* anc, const int64_t* tokens, int tmax, const int* t_dev, void* out,
+                          int ldo, int rows, int heads, float scale, void* stream);
+int spmm_decode_attn_cross(const void* q, int ldq, const void* k, const void* v, int ldkv, int Tk, int group,
+                           const int* kv_len, void* out, int ldo, int rows, int heads, float scale, void* stream);
+int spmm_beam_step(const void* logits, int ld, int V, int k, int tmax, int n_mol, int fin_cap, int cls_id, int sep_id,
+                   int* t_dev, float* scores, int64_t* tokens, int* anc, int64_t* next_ids, float* fin_scores,
+                   int64_t* fin_tokens, int* fin_len, int* fin_count, int* done, float* trace_logp, int* trace_tok,
+                   unsigned int* ticket, void* stream);
+
 /* ------------------------------------------------------------------ host-side WordPiece tokenizer (no CUDA)
  * Replaces BertTokenizer(do_basic_tokenize=False) + WordpieceTokenizer(max_input_chars_per_word=250) as used by
  * SPMM_pretrain.py:19-20 / SPMM_models.py:352 / d_smiles2pv.py:43,61: whitespace split, greedy longest-match-first

@@ -54,6 +54,10 @@ SIGNATURES = {
     "spmm_lm_loss_fwd_bwd": (i32, [vp, vp, i32, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
     "spmm_itm_loss_fwd_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "spmm_mpm_loss_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "spmm_decode_embed": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+    "spmm_decode_attn_self": (i32, [vp, i32, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, f32, vp]),
+    "spmm_decode_attn_cross": (i32, [vp, i32, vp, vp, i32, i32, i32, vp, vp, i32, i32, i32, f32, vp]),
+    "spmm_beam_step": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "spmm_wordpiece_create": (vp, [C.POINTER(C.c_char_p), i32, i32, i32]),
     "spmm_wordpiece_destroy": (None, [vp]),
     "spmm_wordpiece_encode_batch": (i32, [vp, C.POINTER(C.c_char_p), i32, i32, i32, i32, i32, vp, vp, i32]),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OUT = os.path.join(HERE, "libspmm_b200.so")
-SOURCES = ["gemm.cu", "arena.cu", "layernorm.cu", "embed.cu", "itc.cu", "attention.cu", "attention_tc.cu", "losses.cu", "misc.cu", "tokenizer.cu"]
+SOURCES = ["gemm.cu", "arena.cu", "layernorm.cu", "embed.cu", "itc.cu", "attention.cu", "attention_tc.cu", "losses.cu", "misc.cu", "tokenizer.cu", "decode.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-I" + INCLUDE, "-I" + CSRC]
 

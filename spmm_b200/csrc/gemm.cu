@@ -48,6 +48,7 @@ struct GemmParams {
   uint32_t mn_lbo, mn_sbo;  // MN-major descriptor strides (bytes)
   const unsigned long long* salt;  // device RNG salt (may be null)
   int debug_nomma;           // debug: consume stages without issuing MMAs (TMA ingest measurement)
+  int side_tma;              // 1: the bf16 side operand arrives by TMA in the output staging tile; 0: register prefetch
   int splits, kb_per_split;  // split-K (fp32 accumulate outputs only): partials are reduced with red.global.add
   unsigned long long* trace; // debug: per-CTA phase timestamps (16 x u64 per CTA), null in production
 };
@@ -451,7 +452,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // remote a
 }
 
 struct Gemm2Maps {
-  CUtensorMap a, b, c, pre;   // pre: 2nd bf16 output (pre-activation, or gelu' of it)
+  CUtensorMap a, b, c, side, pre;   // side: residual or dGELU factor (bf16, same shape as C); pre: 2nd bf16 output
 };
 
 // One 32-column chunk of this thread's row: fused math on v[32], side operand / result through the staging tile.
@@ -611,7 +612,9 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
   uint64_t* empty_bar = full_bar + kStages2;
   uint64_t* tfull_bar = empty_bar + kStages2;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* side_full = tempty_bar + 2;     // side operand of the current tile landed in the staging tile
+  uint64_t* stage_free = side_full + 1;     // both halves' stores of the previous tile have read the staging tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
   float* s_bias = reinterpret_cast<float*>(staging + STG_BYTES + 512);
 
   pdl_trigger();
@@ -632,6 +635,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
     tma_prefetch_desc(&maps.a);
     tma_prefetch_desc(&maps.b);
     tma_prefetch_desc(&maps.c);
+    if (has_side && p.side_tma) tma_prefetch_desc(&maps.side);
     if (has_pre) tma_prefetch_desc(&maps.pre);
   }
   if (warp == 1 && lane == 0) {
@@ -643,6 +647,8 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       mbar_init(&tfull_bar[s], 1);    // multicast commit
       mbar_init(&tempty_bar[s], 16);  // leader's copy: 8 epilogue warps x 2 CTAs
     }
+    mbar_init(side_full, 1);
+    mbar_init(stage_free, 2);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -730,6 +736,22 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+  } else if (warp == 3 && lane == 0 && has_side && p.side_tma) {
+    // ===================== side-operand loader (both CTAs: own 128 rows) =====================
+    uint32_t ph = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int mn = tile % num_mn;
+      const int m0 = (mn % num_m) * 2 * BM + (int)rank * BM, n0 = (mn / num_m) * BN2;
+      mbar_wait(stage_free, ph ^ 1);   // previous tile's stores have drained the staging tile
+      int nbox = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) nbox += (n0 + 64 * b < p.N) ? 1 : 0;
+      mbar_expect_tx(side_full, nbox * STG_BOX_BYTES);
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (n0 + 64 * b < p.N) tma_load_2d(staging + b * STG_BOX_BYTES, &maps.side, side_full, n0 + 64 * b, m0);
+      ph ^= 1;
+    }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs: own 128 rows x 256 columns) =====================
     const int q = warp & 3;             // TMEM lane quadrant this warp may read
@@ -749,14 +771,15 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       else if (dg && st && !g && !has_pre && p.bias == nullptr && p.drop_thresh16 == 0) mode = EPI_DGELU_MUL;
       else if (!g && !dg && !has_pre) mode = EPI_LINEAR;
     }
-    // The bf16 side operand (residual, or the stored gelu' factor) is read straight from global memory by the thread
-    // that owns the row, one 32-column chunk (64 B) ahead of its use.  It used to arrive by TMA in the output staging
-    // tile, which chained side load -> math -> store drain -> next side load per tile (8 us per tile on the dGELU GEMM
-    // against 5.3 us of mainloop); register prefetch has no such chain and starts before the accumulator is complete.
+    // The bf16 side operand (residual, or the stored gelu' factor) arrives by TMA in the output staging tile
+    // (side_tma: single bf16 output) and is replaced in place by the result; with a 2nd output the staging tile has no
+    // room for it and the thread that owns the row reads it from global memory one 32-column chunk (64 B) ahead.
     const __nv_bfloat16* side = (p.flags & SPMM_GEMM_DGELU) ? p.aux : p.residual;
     const int lds = (p.flags & SPMM_GEMM_DGELU) ? p.ldaux : p.ldr;
+    const bool side_tma = has_side && p.side_tma;
+    const bool side_reg = has_side && !p.side_tma;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, side_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int mn = tile % num_mn;
       const int m0 = (mn % num_m) * 2 * BM + (int)rank * BM, n0 = (mn / num_m) * BN2;
@@ -767,7 +790,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       auto load_side = [&](int col, uint4(&dst)[4]) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (has_side && row_ok && col + 8 * i + 8 <= p.N) dst[i] = __ldg(reinterpret_cast<const uint4*>(side_row + col + 8 * i));
+          if (side_reg && row_ok && col + 8 * i + 8 <= p.N) dst[i] = __ldg(reinterpret_cast<const uint4*>(side_row + col + 8 * i));
           else dst[i] = make_uint4(0u, 0u, 0u, 0u);
         }
       };
@@ -781,6 +804,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
         bar_sync_named(bar_id, 128);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
+      if (side_tma) mbar_wait(side_full, side_phase);
       tc_fence_after();
       if (warp == 4 && lane == 0 && tile == pair) trace_mark(p, 5);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN2 + 128 * h;
@@ -788,6 +812,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
         if (sub > 0) {
           if (elected) bulk_wait_read0();
           bar_sync_named(bar_id, 128);
+          if (warp == 4 && lane == 0 && tile == pair) trace_mark(p, 14);
         }
         const int nchunk = 4 / nsub;
         // TMEM reads are software-pipelined: the load of chunk cc+1 is in flight while chunk cc is processed
@@ -801,7 +826,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
           uint4 side_cur[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) side_cur[i] = side_next[i];
-          if (c + 1 < 4) load_side(col0 + 32, side_next);
+          if (side_reg && c + 1 < 4) load_side(col0 + 32, side_next);
           tmem_ld_wait();
           // staging placement: bf16 -> box 2h + (c >> 1), units 4*(c & 1)..+3; pre mode -> act box 2h+1 / pre box 2h,
           // units 4*cc..+3; f32 -> box 2h + cc, units 0..7
@@ -815,6 +840,10 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
             u0 = 4 * cc;
           } else { out_row = staging + (2 * h + (c >> 1)) * STG_BOX_BYTES + r * 128; u0 = 4 * (c & 1); }
           const bool more = cc + 1 < nchunk && col0 + 32 < p.N;
+          if (side_tma) {   // the side operand sits where the result goes
+#pragma unroll
+            for (int i = 0; i < 4; ++i) side_cur[i] = *reinterpret_cast<const uint4*>(out_row + (((u0 + i) ^ sw) << 4));
+          }
           if (mode != EPI_GENERIC) {
             f32x2 v2[16];
 #pragma unroll
@@ -836,7 +865,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
         }
-        if (warp == 4 && lane == 0 && tile == pair && sub == 0) trace_mark(p, 12);
+        if (warp == 4 && lane == 0 && tile == pair) trace_mark(p, sub == 0 ? 12 : 15);
         fence_proxy_async();
         bar_sync_named(bar_id, 128);
         if (warp == 4 && lane == 0 && tile == pair && sub == 0) trace_mark(p, 13);
@@ -887,7 +916,12 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
           bulk_commit();
         }
       }
+      if (side_tma && elected) {   // let the side loader refill the staging tile for the next tile
+        bulk_wait_read0();
+        mbar_arrive(stage_free);
+      }
       if (warp == 4 && lane == 0) trace_mark(p, tile == pair ? 6 : 10);
+      side_phase ^= 1;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -964,6 +998,8 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
 }
 
 static int g_use_2cta = 1;
+static int g_side_reg = 0;    // debug A/B: 1 = side operand by register prefetch even where TMA staging is possible
+static int g_no_colsum = 0;   // debug A/B: 1 = fused column sums computed by the separate kernel instead
 
 static int launch2(const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st) {
   static bool configured = false;
@@ -1002,6 +1038,8 @@ extern "C" int spmm_gemm_debug_config(int mn_lbo_bytes, int mn_sbo_bytes, int fo
   g_force_bn = force_bn & 0xFFFF;
   g_split_k = (force_bn & 0x10000) ? 0 : 1;   // bit 16 disables split-K (debug / A-B measurements)
   g_use_2cta = (force_bn & 0x40000) ? 0 : 1;  // bit 18 disables the 2-CTA kernel
+  g_side_reg = (force_bn & 0x100000) ? 1 : 0;
+  g_no_colsum = (force_bn & 0x200000) ? 1 : 0;
   g_nomma = (force_bn & 0x20000) ? 1 : ((force_bn & 0x80000) ? 2 : 0);   // bit 19: MMA-only (no TMA, garbage results)     // bit 17: skip MMAs (TMA-only pipeline timing; results are garbage)
   g_max_ctas = max_ctas;
   return 0;
@@ -1071,7 +1109,8 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   // the same result from a separate pass over the bf16 output
   SPMM_ARG(!p.colsum || !out_f32);
   float* colsum_after = nullptr;
-  if (p.colsum && !(use2 && !p.pre)) { colsum_after = p.colsum; p.colsum = nullptr; }
+  if (p.colsum && (!(use2 && !p.pre) || g_no_colsum)) { colsum_after = p.colsum; p.colsum = nullptr; }
+  p.side_tma = (has_side && !p.pre && !out_f32 && !g_side_reg) ? 1 : 0;
   const int bn = use2 ? BN2 : pick_bn(M, N);
   const int slots = use2 ? kNumSMs / 2 : kNumSMs;
   const int tiles_mn = use2 ? ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2) : ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
@@ -1107,7 +1146,12 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
     // epilogue staging boxes: [128 rows][128 bytes] = 64 bf16 or 32 f32 columns
     rc = make_map(&maps.c, C, N, M, ldc, out_f32 ? 32 : 64, BM, out_f32);
     if (rc) return rc;
+    maps.side = maps.c;
     maps.pre = maps.c;
+    if (p.side_tma) {
+      rc = p.aux ? make_map(&maps.side, p.aux, N, M, p.ldaux, 64, BM) : make_map(&maps.side, p.residual, N, M, p.ldr, 64, BM);
+      if (rc) return rc;
+    }
     if (p.pre) {
       rc = make_map(&maps.pre, p.pre, N, M, p.ldp, 64, BM);
       if (rc) return rc;

@@ -280,3 +280,35 @@ def pv_tokens_bwd(dprop, pv, mpm_mask, dw, db, dcls, dmask):
 def set_rng_salt(dev_tensor):
     """Registers the device int64 scalar the kernels add to every dropout / sampler seed (None clears it)."""
     call("spmm_set_rng_salt_ptr", _p(dev_tensor))
+
+
+# ---------------------------------------------------------------------------------------------- single-token decode
+def decode_embed(ids, t_dev, word, pos, type0, H):
+    x = torch.empty(ids.numel(), H, device=ids.device, dtype=BF16)
+    call("spmm_decode_embed", ids.data_ptr(), t_dev.data_ptr(), word.data_ptr(), pos.data_ptr(), type0.data_ptr(),
+         x.data_ptr(), ids.numel(), H, _st())
+    return x
+
+
+def decode_attn_self(q, k_new, v_new, cache_k, cache_v, anc, tokens, t_dev, out, heads, scale):
+    rows, tmax = tokens.shape
+    assert k_new.stride(0) == v_new.stride(0) and cache_k.is_contiguous() and cache_v.is_contiguous()
+    call("spmm_decode_attn_self", q.data_ptr(), q.stride(0), k_new.data_ptr(), v_new.data_ptr(), k_new.stride(0),
+         cache_k.data_ptr(), cache_v.data_ptr(), anc.data_ptr(), tokens.data_ptr(), tmax, t_dev.data_ptr(), out.data_ptr(),
+         out.stride(0), rows, heads, float(scale), _st())
+    return out
+
+
+def decode_attn_cross(q, k, v, Tk, group, out, heads, scale, kv_len=None):
+    assert k.stride(0) == v.stride(0)
+    call("spmm_decode_attn_cross", q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), Tk, group,
+         _p(kv_len), out.data_ptr(), out.stride(0), q.shape[0], heads, float(scale), _st())
+    return out
+
+
+def beam_step(logits, V, st, cls_id, sep_id):
+    """`st`: the device-side beam state (spmm_b200/generate.py:BeamState)."""
+    call("spmm_beam_step", logits.data_ptr(), logits.stride(0), V, st.k, st.tmax, st.n_mol, st.fin_cap, cls_id, sep_id,
+         st.t_dev.data_ptr(), st.scores.data_ptr(), st.tokens.data_ptr(), st.anc.data_ptr(), st.next_ids.data_ptr(),
+         st.fin_scores.data_ptr(), st.fin_tokens.data_ptr(), st.fin_len.data_ptr(), st.fin_count.data_ptr(),
+         st.done.data_ptr(), _p(st.trace_logp), _p(st.trace_tok), st.ticket.data_ptr(), _st())

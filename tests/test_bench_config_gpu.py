@@ -129,7 +129,7 @@ def test_graphed_training_step_on_bucketed_lengths_equals_eager_step():
     print("eager", out["eager"][0].tolist())
     print("graph", out["graph"][0].tolist())
     assert out["graph"][3] == 1                                  # both widths (<= 64) share ONE graph
-    assert torch.allclose(out["eager"][0], out["graph"][0], atol=2e-3)
+    assert torch.allclose(out["eager"][0], out["graph"][0], atol=2e-3, rtol=2e-4)
     ge, gg = out["eager"][1][0], out["graph"][1][0]
     print("step-1 gradient rel-L2 eager (unpadded) vs graph (bucket-padded): %.2e" % float((ge - gg).norm() / ge.norm()))
     assert float((ge - gg).norm() / ge.norm()) < 1e-3

@@ -7,7 +7,8 @@ from spmm_b200 import kernels as K, _lib
 
 DEV, BF = "cuda", torch.bfloat16
 NAMES = ["entry", "setup done", "1st TMA issued", "1st full", "tile0 MMAs committed", "tile0 tfull seen", "tile0 epi done",
-         "pre-exit sync", "exit", "producer done", "last epi done", "-", "tile0 sub0 chunks done", "tile0 sub0 barrier passed"]
+         "pre-exit sync", "exit", "producer done", "last epi done", "-", "tile0 sub0 chunks done", "tile0 sub0 barrier passed",
+         "tile0 sub1 start (prev store read)", "tile0 sub1 chunks done"]
 T, H, I = 6144, 768, 3072
 CASES = [("dgrad out (plain)", T, H, H, dict(b_mn=True)),
          ("fwd out+res+drop", T, H, H, dict(bias=True, residual=True, dropout_p=0.1)),
@@ -15,6 +16,7 @@ CASES = [("dgrad out (plain)", T, H, H, dict(b_mn=True)),
          ("fwd ffn-up gelu+pre", T, I, H, dict(bias=True, gelu=True, pre=True)),
          ("fwd ffn-down", T, H, I, dict(bias=True, residual=True, dropout_p=0.1)),
          ("dgrad ffn2+dgelu", T, I, H, dict(b_mn=True, dgelu=True)),
+         ("dgrad ffn2+dgelu+colsum", T, I, H, dict(b_mn=True, dgelu=True, colsum=True)),
          ("wgrad ffn1", I, H, T, dict(a_mn=True, b_mn=True, wgrad=True))]
 trace = torch.zeros(148 * 16, dtype=torch.int64, device=DEV)
 for name, M, N, Kd, kw in CASES:
@@ -26,11 +28,13 @@ for name, M, N, Kd, kw in CASES:
     res = torch.randn(M, N, device=DEV).to(BF) if kw.get("residual") else None
     pre = torch.empty(M, N, device=DEV, dtype=BF) if kw.get("pre") else None
     dg = torch.randn(M, N, device=DEV).to(BF) if kw.get("dgelu") else None
+    cs = torch.zeros(N, device=DEV) if kw.get("colsum") else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
 
     def run():
         K.gemm(A, B, M, N, Kd, a_mn=a_mn, b_mn=b_mn, out=out, out_f32=wgrad, accumulate=wgrad, bias=bias, residual=res,
-               pre_act_out=pre, dgelu_pre=dg, gelu=kw.get("gelu", False), dropout_p=kw.get("dropout_p", 0.0), seed=123)
+               pre_act_out=pre, dgelu_pre=dg, gelu=kw.get("gelu", False), dropout_p=kw.get("dropout_p", 0.0), seed=123,
+               dgelu_stored=bool(kw.get("dgelu") or kw.get("pre")), colsum_out=cs)
     for _ in range(3):
         run()
     for cold in (0, 1):
