@@ -1,8 +1,20 @@
-"""Inference drivers over the sub-module API, mirroring the reference's d_smiles2pv.py:14-52 (SMILES -> 53 property
-values, autoregressive over the property tokens) and d_pv2smiles_batched.py:17-59 + d_pv2smiles_single.py:26-51
-(property vector -> SMILES, beam search with k beams over the fusion decoder).  Host logic only: every encoder pass goes
-through the same sm_100a kernels as pre-training (no KV cache yet - SURVEY.md section 8f ranks that next)."""
+"""Inference drivers mirroring the reference's d_smiles2pv.py:14-52 (SMILES -> 53 property values, autoregressive over
+the property tokens) and d_pv2smiles_batched.py:17-59 + d_pv2smiles_single.py:26-51 (property vector -> SMILES, beam
+search with k beams over the fusion decoder).
+
+Two layers:
+  * the reference-shaped loops over the sub-module API (`smiles2pv`, `pv2smiles`: what the d_*.py scripts do, every
+    pass through the same sm_100a kernels as pre-training, full prefix recomputed per token like the reference), and
+  * `PvDecoder` / `pv2smiles_batched`: the B200-native decode path - KV-cached single-token steps for MANY molecules'
+    beams at once, cross K/V of the 54 property tokens projected once per molecule, beam bookkeeping on the device
+    (csrc/decode.cu), the whole step captured in ONE CUDA graph that is replayed per token with no host sync.
+"""
+import math
+
 import torch
+
+from . import kernels as K
+from . import ops
 
 
 def _pv_step(model, prop_input, text_embeds, text_atts):
@@ -78,3 +90,181 @@ def pv2smiles(model, prop, cls_id=2, sep_id=3, k=2, stochastic=False, max_steps=
         beams = cand.flatten(0, 1)[flat]
     finished.sort(key=lambda item: item[0], reverse=True)
     return finished[:k]
+
+
+# ====================================================================================================================
+# KV-cached batched beam decode (B200-native path for d_pv2smiles_batched.py:24-59)
+class BeamState:
+    """Device-side beam-search state consumed by `spmm_beam_step` (csrc/decode.cu): k live beams per molecule."""
+
+    def __init__(self, n_mol, k, tmax, device, trace_steps=0):
+        self.n_mol, self.k, self.tmax, self.fin_cap = n_mol, k, tmax, k * k + k
+        R = n_mol * k
+        i32, i64, f32 = dict(device=device, dtype=torch.int32), dict(device=device, dtype=torch.int64), dict(device=device, dtype=torch.float32)
+        self.t_dev = torch.zeros(1, **i32)
+        self.scores = torch.zeros(n_mol, k, **f32)
+        self.tokens = torch.zeros(R, tmax, **i64)
+        self.anc = torch.zeros(R, tmax, **i32)
+        self.next_ids = torch.zeros(R, **i64)
+        self.fin_scores = torch.zeros(n_mol, self.fin_cap, **f32)
+        self.fin_tokens = torch.zeros(n_mol, self.fin_cap, tmax, **i64)
+        self.fin_len = torch.zeros(n_mol, self.fin_cap, **i32)
+        self.fin_count = torch.zeros(n_mol, **i32)
+        self.done = torch.zeros(n_mol, **i32)
+        self.ticket = torch.zeros(1, **i32)
+        self.trace_logp = torch.zeros(trace_steps, R, k, **f32) if trace_steps else None
+        self.trace_tok = torch.zeros(trace_steps, R, k, **i32) if trace_steps else None
+
+    def reset(self, cls_id):
+        for t in (self.t_dev, self.scores, self.tokens, self.anc, self.fin_scores, self.fin_tokens, self.fin_len,
+                  self.fin_count, self.done):
+            t.zero_()
+        self.tokens[:, 0] = cls_id
+        self.next_ids.fill_(cls_id)
+
+
+class PvDecoder:
+    """k-beam PV -> SMILES decoding of `n_mol` molecules at a time (rows = n_mol * k live beams).
+
+    Per generated token ONE graph replay: embedding of the new token at position t, 12 decoder layers on [rows, H]
+    (fused QKV GEMM -> cached causal self-attention -> output GEMM + residual -> LayerNorm; for the 6 fusion layers a
+    query GEMM -> cross-attention over the molecule's 54 cached property keys -> output GEMM + LayerNorm; FFN), LM head,
+    device-side beam update.  The reference recomputes the whole prefix for every token (d_pv2smiles_single.py:29-36);
+    the stack is causal, so the cached path computes the same last-position logits."""
+
+    def __init__(self, model, n_mol, k=2, tmax=104, trace_steps=0, use_graph=True):
+        self.model, self.n_mol, self.k, self.tmax = model, n_mol, k, tmax
+        te = model.text_encoder
+        self.bd = te.bert._bundles()
+        cfg = te.config
+        self.H, self.heads, self.V, self.ld = cfg.hidden_size, cfg.num_attention_heads, cfg.vocab_size, te.logit_ld()
+        self.I = cfg.intermediate_size
+        dev = model.arena().device
+        self.dev = dev
+        R = n_mol * k
+        self.R = R
+        self.state = BeamState(n_mol, k, tmax, dev, trace_steps)
+        nl = len(self.bd.layers)
+        self.cache_k = [torch.zeros(tmax, R, self.H, device=dev, dtype=torch.bfloat16) for _ in range(nl)]
+        self.cache_v = [torch.zeros(tmax, R, self.H, device=dev, dtype=torch.bfloat16) for _ in range(nl)]
+        self.n_pv = 54
+        self.cross_kv = {i: torch.zeros(n_mol * self.n_pv, 2 * self.H, device=dev, dtype=torch.bfloat16)
+                         for i, lw in enumerate(self.bd.layers) if lw.cross is not None}
+        self.use_graph = use_graph
+        self.graph = None
+        self.scale = 1.0 / math.sqrt(self.H // self.heads)
+
+    # ---- once per batch of molecules: property encoder + cross K/V of its 54 tokens for the 6 fusion layers
+    @torch.no_grad()
+    def encode(self, prop):
+        from .xbert import raw_outputs
+        m = self.model
+        assert prop.shape[0] == self.n_mol
+        tokens = torch.cat([m.property_cls.expand(prop.shape[0], -1, -1), m.property_embed(prop.unsqueeze(2))], dim=1)
+        assert tokens.shape[1] == self.n_pv
+        with raw_outputs():
+            pe = m.property_encoder(inputs_embeds=tokens, return_dict=True).last_hidden_state      # [N, 54, H] bf16
+        pe2 = pe.reshape(self.n_mol * self.n_pv, self.H)
+        for i, buf in self.cross_kv.items():
+            C = self.bd.layers[i].cross
+            K.gemm(pe2, C.wkv, pe2.shape[0], 2 * self.H, self.H, bias=C.bkv, out=buf)
+
+    def _ln(self, x, W):
+        return K.layernorm_fwd(x, W.ln_g, W.ln_b, W.eps, save_stats=False)[0]
+
+    # ---- one token for every live beam (the captured graph body)
+    def _step(self):
+        st, bd, R, H = self.state, self.bd, self.R, self.H
+        emb = bd.emb
+        x = K.decode_embed(st.next_ids, st.t_dev, emb.word, emb.pos, emb.type0, H)
+        x = self._ln(x, emb)
+        for i, lw in enumerate(bd.layers):
+            W = lw.attn
+            qkv = K.gemm(x, W.wqkv, R, 3 * H, H, bias=W.bqkv)
+            o = torch.empty(R, H, device=self.dev, dtype=torch.bfloat16)
+            K.decode_attn_self(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], self.cache_k[i], self.cache_v[i], st.anc, st.tokens,
+                               st.t_dev, o, self.heads, self.scale)
+            x = self._ln(K.gemm(o, W.wo, R, H, H, bias=W.bo, residual=x), W)
+            if lw.cross is not None:
+                C = lw.cross
+                q = K.gemm(x, C.wq, R, H, H, bias=C.bq)
+                kv = self.cross_kv[i]
+                o2 = torch.empty(R, H, device=self.dev, dtype=torch.bfloat16)
+                K.decode_attn_cross(q, kv[:, :H], kv[:, H:], self.n_pv, self.k, o2, self.heads, self.scale)
+                x = self._ln(K.gemm(o2, C.wo, R, H, H, bias=C.bo, residual=x), C)
+            F_ = lw.ffn
+            act = K.gemm(x, F_.w1, R, self.I, H, bias=F_.b1, gelu=True)
+            x = self._ln(K.gemm(act, F_.w2, R, H, self.I, bias=F_.b2, residual=x), F_)
+        logits = ops.lm_logits(x, bd.head, self.V, self.ld)
+        K.beam_step(logits, self.V, st, 0, self.sep_id)
+        return logits
+
+    @torch.no_grad()
+    def generate(self, prop, cls_id=2, sep_id=3, max_steps=100, on_step=None):
+        """Beam search for prop [n_mol, 53]; returns, per molecule, up to k (log-prob, token ids incl. [CLS] .. [SEP])
+        pairs, best first (d_pv2smiles_batched.py:24-52).  `on_step(t, logits)` (eager mode only) observes each step."""
+        self.model.eval()
+        self.sep_id = sep_id
+        st = self.state
+        st.reset(cls_id)
+        self.encode(prop)
+        n_steps = min(max_steps + 1, self.tmax - 2)
+        if st.trace_logp is not None:
+            n_steps = min(n_steps, st.trace_logp.shape[0])
+        if self.use_graph and on_step is None:
+            if self.graph is None:
+                self._step()                                   # warm-up (lazy kernel attributes); state is reset below
+                torch.cuda.synchronize()
+                st.reset(cls_id)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._step()
+            for t in range(n_steps):
+                self.graph.replay()
+                if t % 16 == 15 and bool(st.done.all()):       # one sync per 16 tokens
+                    break
+        else:
+            for t in range(n_steps):
+                logits = self._step()
+                if on_step is not None:
+                    on_step(t, logits)
+                if t % 16 == 15 and bool(st.done.all()):
+                    break
+        cnt = st.fin_count.tolist()
+        sc, ln, tk = st.fin_scores.cpu(), st.fin_len.cpu(), st.fin_tokens.cpu()
+        out = []
+        for m in range(self.n_mol):
+            items = [(float(sc[m, e]), tk[m, e, :int(ln[m, e])].clone()) for e in range(min(cnt[m], st.fin_cap))]
+            items.sort(key=lambda it: it[0], reverse=True)     # stable, like sorted(final_output, key=p, reverse=True)
+            out.append(items[:self.k])
+        return out
+
+
+_DECODERS = {}
+
+
+@torch.no_grad()
+def pv2smiles_batched(model, prop, cls_id=2, sep_id=3, k=2, max_steps=100):
+    """d_pv2smiles_batched.py:24-52 for a whole batch prop [N, 53] at once (deterministic beams): list of N result lists."""
+    key = (id(model), prop.shape[0], k)
+    dec = _DECODERS.get(key)
+    if dec is None or dec.model is not model:
+        dec = _DECODERS[key] = PvDecoder(model, prop.shape[0], k=k)
+    return dec.generate(prop.to(model.arena().device).float(), cls_id, sep_id, max_steps)
+
+
+@torch.no_grad()
+def evaluate_pv2smiles(model, data_loader, tokenizer, k=2):
+    """`evaluate` of d_pv2smiles_batched.py:17-59: (reference SMILES, best generated SMILES) per molecule; every loader
+    batch is decoded at once."""
+    reference, candidate = [], []
+    for prop, text in data_loader:
+        res = pv2smiles_batched(model, prop, tokenizer.cls_token_id, tokenizer.sep_token_id, k=k)
+        for b, items in enumerate(res):
+            reference.append(text[b].replace('[CLS]', ''))
+            if items:
+                sent = items[0][1]
+                candidate.append(tokenizer.convert_tokens_to_string(tokenizer.convert_ids_to_tokens(sent[:-1])).replace('[CLS]', ''))
+            else:
+                candidate.append('')
+    return reference, candidate

@@ -143,7 +143,8 @@ def test_gemm_epilogues():
     assert rel_err(o1[nz], (ref_pre / 0.9)[nz]) < 6e-3
 
 
-@pytest.mark.parametrize("M,N,K_", [(6144, 3072, 768), (5184, 2304, 768), (6144, 768, 3072), (1000, 300, 768), (390, 520, 136)])
+@pytest.mark.parametrize("M,N,K_", [(6144, 3072, 768), (5184, 2304, 768), (6144, 768, 3072), (1000, 300, 768), (390, 520, 136),
+                                    (390, 784, 136)])
 def test_gemm_epilogues_multi_tile(M, N, K_):
     """Staged (TMA-store) epilogue of the 2-CTA kernel over several tiles per CTA pair, ragged edges and padded ldc."""
     a, w = rnd(M, K_, dtype=BF, seed=11), rnd(N, K_, dtype=BF, seed=12, scale=0.05)
