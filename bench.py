@@ -585,6 +585,128 @@ def kernel_rooflines(torch, kernels, model, step_fn, B, world, graph_args=None):
     return roof, extra
 
 
+# ------------------------------------------------------------------------------------------- configs #4 / #5 (inference)
+def run_decode(args):
+    """BASELINE.json configs[3] / configs[4]: `--workload smiles2pv` (d_smiles2pv.py: 64 tokenised SMILES of length 64 ->
+    53 property values each) and `--workload pv2smiles` (d_pv2smiles_batched.py: 64 property vectors, k = 2 beams, 101
+    generated tokens - random-init weights never emit [SEP], so every molecule runs the reference's full 1 + 100
+    expansions).  One "step" = one whole generation for the batch.  `value`: inputs resident in HBM; `e2e`: pinned host
+    inputs copied in and results read back every step.  Beside it: the reference-shaped loop over the same kernels
+    (full prefix recomputed per token, one molecule at a time for the beam search, like the reference) and the oracle
+    port (eager PyTorch, autocast bf16) on this GPU, on a bounded sample."""
+    import torch
+    import torch.distributed as dist
+    from spmm_b200 import _lib, generate, ops, synth
+    from spmm_b200.SPMM_models import SPMM
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import datetime
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    tj, pj = os.path.join(CFG, "config_bert.json"), os.path.join(CFG, "config_bert_property.json")
+    model = SPMM(config=synth.pretrain_config(tj, pj, queue_size=96, batch_size=8))
+    synth.fill_by_name(model)
+    model.to(dev)
+    model.build_arenas(dev)
+    model.eval()
+    N = args.batch if args.batch != 96 else 64
+    pv_h, ids_h, mask_h, _ = synth.synthetic_batch(N, seed=1234 + rank, fixed_len=args.seq_len)
+    pv_h, ids_h, mask_h = pv_h.pin_memory(), ids_h.pin_memory(), mask_h.pin_memory()
+    pv, ids, mask = pv_h.to(dev), ids_h.to(dev), mask_h.to(dev)
+    k = 2
+    if args.workload == "smiles2pv":
+        fast = lambda host: generate.smiles2pv_fast(model, ids_h if host else ids, mask_h if host else mask)
+        slow = lambda n: generate.smiles2pv(model, ids[:n], mask[:n])
+        what = "SMILES->PV (d_smiles2pv.py): %d SMILES of %d tokens -> 53 autoregressive property predictions each" % (N, args.seq_len)
+        h2d, d2h = ids_h.numel() * 16, N * 53 * 4
+        n_slow = N
+    else:
+        fast = lambda host: generate.pv2smiles_batched(model, pv_h if host else pv, k=k)
+        slow = lambda n: [generate.pv2smiles(model, pv[i:i + 1], k=k) for i in range(n)]
+        what = "PV->SMILES (d_pv2smiles_batched.py): %d property vectors, k=%d beam search, 1 + 100 token expansions each" % (N, k)
+        h2d, d2h = pv_h.numel() * 4, N * 12 * 104 * 8
+        n_slow = 2
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync(); e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record(); sync()
+        return e0.elapsed_time(e1) / steps, out
+    for _ in range(max(args.warmup, 1)):
+        fast(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    ms, _ = timed(lambda: fast(False), args.steps)
+    launches = _lib.launch_count()                 # kernels launched from Python (encoders, cross K/V projections)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, res = timed(lambda: fast(True), args.steps)
+    # kernels inside the replayed graphs: count one eager token step and multiply by the replays
+    _lib.reset_launch_count()
+    if args.workload == "smiles2pv":
+        next(iter(generate._S2P.values()))._step(56)
+        launches += args.steps * 53 * _lib.launch_count()
+    else:
+        next(iter(generate._DECODERS.values()))._step()
+        launches += args.steps * 101 * _lib.launch_count()
+    torch.cuda.synchronize()
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            shutdown_distributed(dist, torch)
+        return
+    line = {"metric": "%s molecules/sec" % args.workload, "value": N * world / (ms / 1e3), "unit": "molecules/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": what + "; reference config_bert*.json shapes, name-seeded random-init weights", "global_batch": N * world,
+                       "seq_len": args.seq_len, "parallelism": "replicas x%d (independent molecules, no collective)" % world,
+                       "l2": "weights 0.3 GB bf16 + KV caches >> 126 MB L2 per generation; no explicit flush"},
+            "e2e": {"value": N * world / (ms_e2e / 1e3), "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "launch_mode": "cuda_graph per token step (captured once, replayed)", "clocks": clocks,
+            "peaks": peaks()}
+    if not args.no_cpu_baseline and world == 1:
+        slow(1)
+        ms_slow, _ = timed(lambda: slow(n_slow), 1)
+        line["same_kernels_full_prefix_loop"] = {"value": n_slow / (ms_slow / 1e3), "unit": "molecules/s",
+                                                 "what": "the reference-shaped loop (spmm_b200.generate.%s) over the same sm_100a kernels: whole prefix "
+                                                         "recomputed per token, eager launches, %d molecule(s)" % (
+                                                             "smiles2pv" if args.workload == "smiles2pv" else "pv2smiles, one molecule at a time", n_slow)}
+        try:
+            import json as _json
+            from oracle import generate_ref, spmm_ref
+            P = spmm_ref.state_from_model(model, device=dev, requires_grad=False)
+            ct, cp = _json.load(open(tj)), _json.load(open(pj))
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                if args.workload == "smiles2pv":
+                    f = lambda: generate_ref.smiles2pv(P, ct, cp, ids, mask)
+                    n_ref = N
+                else:
+                    f = lambda: generate_ref.pv2smiles_beam(P, ct, cp, pv[:1], k=k)
+                    n_ref = 1
+                f()
+                ms_ref, _ = timed(f, 1)
+            line["gpu_eager_baseline"] = {"value": n_ref / (ms_ref / 1e3), "unit": "molecules/s", "kind": "port",
+                                          "what": "oracle/generate_ref.py (the reference's loop, eager PyTorch) on this GPU under "
+                                                  "torch.autocast(bfloat16), %d molecule(s)" % n_ref}
+        except Exception as ex:                                  # noqa: BLE001
+            line["gpu_eager_baseline"] = {"unavailable": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -597,9 +719,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch kernels from Python instead of replaying the step's CUDA graph")
     ap.add_argument("--profile", action="store_true", help="bare loop for ncu: no e2e / instrumented / CPU legs")
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "smiles2pv", "pv2smiles"],
+                    help="pretrain = the headline metric (BASELINE.json configs[1]); smiles2pv / pv2smiles = configs[3] / [4]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "pretrain":
+        run_decode(args)
     else:
         if not args.profile:
             args.warmup = max(args.warmup, 3)

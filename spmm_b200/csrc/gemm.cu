@@ -425,7 +425,6 @@ __device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* 
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -762,15 +761,10 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
     const int r = q * 32 + lane;        // row within this CTA's 128-row tile
     const int sw = r & 7;
     const uint32_t drop_key = p.drop_thresh16 ? fold_seed(salted(p.drop_seed, p.salt)) : 0u;
-    // f32 output: two 64-column sub-phases (a 32-column f32 chunk fills a whole staging box).
-    // 2nd bf16 output (`pipe`): four 32-column sub-phases through a 2-deep ring of [pre | act] half-boxes
-    // ([128 rows][64 B], SWIZZLE_64B) per column half, so the bulk stores of one sub-phase drain while the next one
-    // computes - with two 64-column sub-phases sharing one buffer the phase trace showed 2 x 1.6 us of exposed
-    // store-read waits per tile on the FFN-up GEMM (8.5 us per tile against 5.3 us of mainloop).
-    const bool pipe = has_pre && !out_f32;
-    const int nsub = pipe ? 4 : (out_f32 ? 2 : 1);
-    const int sw64 = (r >> 1) & 3;
-    uint32_t ring = 0;
+    // 64-column sub-phases when a chunk needs two boxes' worth of staging (f32 output, or a 2nd bf16 output).
+    // (Tried: four 32-column sub-phases through a 2-deep ring of [128 rows][64 B] half-boxes so that the store drain of
+    // one sub-phase overlaps the next - the narrower bulk stores made the FFN-up GEMM slower, 48 vs 44 us.)
+    const int nsub = (out_f32 || has_pre) ? 2 : 1;
     // fast path selection (warp-uniform, once per kernel): packed-pair math for the shapes that carry the step
     int mode = EPI_GENERIC;
     if (p.alpha == 1.f && !out_f32) {
@@ -804,7 +798,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       };
       load_side(nh0, side_next);        // in flight while the MMAs of this tile are still running
       // staging boxes of this half are free (previous stores have read them) and the previous bias reads are done
-      if (elected) { if (pipe) bulk_wait_read1(); else bulk_wait_read0(); }
+      if (elected) bulk_wait_read0();
       bar_sync_named(bar_id, 128);
       if (p.bias != nullptr) {
         const int t = threadIdx.x - 128 - 128 * h;
@@ -822,9 +816,9 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       if (nh0 < p.N) tmem_ld32(taddr, rr);
       for (int sub = 0; sub < nsub; ++sub) {
         if (sub > 0) {
-          if (elected) { if (pipe) bulk_wait_read1(); else bulk_wait_read0(); }
+          if (elected) bulk_wait_read0();
           bar_sync_named(bar_id, 128);
-          if (warp == 4 && lane == 0 && tile == pair && sub == 1) trace_mark(p, 14);
+          if (warp == 4 && lane == 0 && tile == pair) trace_mark(p, 14);
         }
         const int nchunk = 4 / nsub;
 #pragma unroll 1
@@ -841,13 +835,12 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
           // units 4*cc..+3; f32 -> box 2h + cc, units 0..7
           uint8_t* out_row;
           uint8_t* pre_row = nullptr;
-          int u0, swz = sw;
+          int u0;
           if (out_f32) { out_row = staging + (2 * h + cc) * STG_BOX_BYTES + r * 128; u0 = 0; }
-          else if (pipe) {                            // ring slot: [pre half-box 8 KB][act half-box 8 KB], 64-byte rows
-            uint8_t* slot = staging + (2 * h + (ring & 1)) * STG_BOX_BYTES;
-            pre_row = slot + r * 64;
-            out_row = slot + STG_BOX_BYTES / 2 + r * 64;
-            u0 = 0; swz = sw64;
+          else if (has_pre) {
+            out_row = staging + (2 * h + 1) * STG_BOX_BYTES + r * 128;
+            pre_row = staging + (2 * h) * STG_BOX_BYTES + r * 128;
+            u0 = 4 * cc;
           } else { out_row = staging + (2 * h + (c >> 1)) * STG_BOX_BYTES + r * 128; u0 = 4 * (c & 1); }
           const bool more = c + 1 < 4 && col0 + 32 < p.N;
           if (side_tma) {   // the side operand sits where the result goes
@@ -859,15 +852,15 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v2[j] = pk2(__uint_as_float(rr[2 * j]), __uint_as_float(rr[2 * j + 1]));
             if (more) tmem_ld32(taddr + (c + 1) * 32, rr);
-            if (mode == EPI_GELU_GRAD) epi2_gelu_grad(v2, s_bias + 128 * h + 32 * c, out_row, pre_row, u0, swz);
-            else if (mode == EPI_DGELU_MUL) epi2_dgelu_mul(v2, side_cur, out_row, u0, swz);
-            else epi2_linear(p, v2, s_bias + 128 * h + 32 * c, m0 + r, col0, drop_key, has_side, side_cur, out_row, u0, swz);
+            if (mode == EPI_GELU_GRAD) epi2_gelu_grad(v2, s_bias + 128 * h + 32 * c, out_row, pre_row, u0, sw);
+            else if (mode == EPI_DGELU_MUL) epi2_dgelu_mul(v2, side_cur, out_row, u0, sw);
+            else epi2_linear(p, v2, s_bias + 128 * h + 32 * c, m0 + r, col0, drop_key, has_side, side_cur, out_row, u0, sw);
           } else {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
             if (more) tmem_ld32(taddr + (c + 1) * 32, rr);
-            epi2_chunk(p, v, s_bias + 128 * h + 32 * c, m0 + r, col0, drop_key, out_row, pre_row, u0, swz, has_side, side_cur);
+            epi2_chunk(p, v, s_bias + 128 * h + 32 * c, m0 + r, col0, drop_key, out_row, pre_row, u0, sw, has_side, side_cur);
           }
         }
         if (sub == nsub - 1) {            // accumulator fully read: hand the TMEM buffer back to the MMA issuer
@@ -890,12 +883,10 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
                 else
                   tma_store_2d(&maps.c, staging + (2 * h + b) * STG_BOX_BYTES, cs + 32 * b, m0);
               }
-          } else if (pipe) {
-            const int c32 = nh0 + 32 * sub;
-            if (c32 < p.N) {
-              uint8_t* slot = staging + (2 * h + (ring & 1)) * STG_BOX_BYTES;
-              tma_store_2d(&maps.pre, slot, c32, m0);
-              tma_store_2d(&maps.c, slot + STG_BOX_BYTES / 2, c32, m0);
+          } else if (has_pre) {
+            if (cs < p.N) {
+              tma_store_2d(&maps.pre, staging + (2 * h) * STG_BOX_BYTES, cs, m0);
+              tma_store_2d(&maps.c, staging + (2 * h + 1) * STG_BOX_BYTES, cs, m0);
             }
           } else {
 #pragma unroll
@@ -904,7 +895,6 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
           }
           bulk_commit();
         }
-        ++ring;
         if (p.colsum != nullptr && !out_f32 && !has_pre) {
           // Column sums of this CTA's 128 x 128 half-tile from the staged bf16 values (what a separate pass over the
           // stored tensor would read), while the bulk store drains: thread = (column pair, row half), 64 rows each,
@@ -978,7 +968,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows with leading dimension `ld` elements.
 static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                    uint32_t box_outer, bool f32 = false, bool swizzle64 = false) {
+                    uint32_t box_outer, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return -2;
   cuuint64_t dims[2] = {inner, outer};
@@ -986,8 +976,8 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t ou
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -3;
 }
 
@@ -1163,10 +1153,8 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (use2) {
-    // epilogue staging boxes: [128 rows][128 bytes] = 64 bf16 or 32 f32 columns; with a 2nd bf16 output both outputs
-    // leave through 32-column half-boxes ([128 rows][64 bytes], SWIZZLE_64B)
-    const bool pipe = p.pre != nullptr && !out_f32;
-    rc = pipe ? make_map(&maps.c, C, N, M, ldc, 32, BM, false, true) : make_map(&maps.c, C, N, M, ldc, out_f32 ? 32 : 64, BM, out_f32);
+    // epilogue staging boxes: [128 rows][128 bytes] = 64 bf16 or 32 f32 columns
+    rc = make_map(&maps.c, C, N, M, ldc, out_f32 ? 32 : 64, BM, out_f32);
     if (rc) return rc;
     maps.side = maps.c;
     maps.pre = maps.c;
@@ -1175,7 +1163,7 @@ extern "C" int spmm_gemm_bf16(const void* A, int lda, int a_mn_major, const void
       if (rc) return rc;
     }
     if (p.pre) {
-      rc = make_map(&maps.pre, p.pre, N, M, p.ldp, 32, BM, false, true);
+      rc = make_map(&maps.pre, p.pre, N, M, p.ldp, 64, BM);
       if (rc) return rc;
     }
     rc = launch2(maps, p, st);

@@ -202,7 +202,7 @@ class PvDecoder:
     @torch.no_grad()
     def generate(self, prop, cls_id=2, sep_id=3, max_steps=100, on_step=None):
         """Beam search for prop [n_mol, 53]; returns, per molecule, up to k (log-prob, token ids incl. [CLS] .. [SEP])
-        pairs, best first (d_pv2smiles_batched.py:24-52).  `on_step(t, logits)` (eager mode only) observes each step."""
+        pairs, best first (d_pv2smiles_batched.py:24-52).  `on_step` (eager mode only) is called as on_step(t, None) before and on_step(t, logits) after each step."""
         self.model.eval()
         self.sep_id = sep_id
         st = self.state
@@ -225,6 +225,8 @@ class PvDecoder:
                     break
         else:
             for t in range(n_steps):
+                if on_step is not None:
+                    on_step(t, None)                           # state before the step (prefixes that are fed)
                 logits = self._step()
                 if on_step is not None:
                     on_step(t, logits)
@@ -268,3 +270,134 @@ def evaluate_pv2smiles(model, data_loader, tokenizer, k=2):
             else:
                 candidate.append('')
     return reference, candidate
+
+
+# ====================================================================================================================
+# SMILES -> PV with cached text-side cross K/V (B200-native path for d_smiles2pv.py:14-52)
+class Smiles2PvDecoder:
+    """53 autoregressive property predictions for a batch of B tokenised SMILES.
+
+    What can be cached is cached: the text encoder runs once, and the keys / values every fusion layer derives from its
+    output (6 x [B*L, 2H]) are projected once instead of 53 times.  The property side cannot be cached - the PV encoder
+    is bidirectional over the growing prefix, so every earlier position changes when a token is appended (the reference
+    recomputes it too, d_smiles2pv.py:15) - but each step is ONE CUDA-graph replay: the prefix lives in a fixed-size
+    buffer (three length buckets 16 / 32 / 56), its current length is a device scalar that feeds the attention
+    kernels' key lengths, the last-position gather and the write of the next token, so no step syncs with the host."""
+
+    BUCKETS = (16, 32, 56)
+    TMAX = 56
+
+    def __init__(self, model, B, L):
+        self.model, self.B, self.L = model, B, L
+        te, pe = model.text_encoder, model.property_encoder
+        self.tb, self.pb = te.bert._bundles(), pe._bundles()
+        cfg = te.config
+        self.H, self.heads, self.I = cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size
+        self.fl = cfg.fusion_layer
+        dev = model.arena().device
+        self.dev = dev
+        H = self.H
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        self.prop_in = torch.zeros(B, self.TMAX, H, **bf)
+        self.t_dev = torch.ones(1, device=dev, dtype=torch.int32)             # current prefix length T
+        self.kv_len_pv = torch.ones(B, device=dev, dtype=torch.int32)
+        self.text_len = torch.zeros(B, device=dev, dtype=torch.int32)
+        self.cross_kv = [torch.zeros(B * L, 2 * H, **bf) for _ in range(self.fl, cfg.num_hidden_layers)]
+        self.preds = torch.zeros(B, 53, device=dev, dtype=torch.float32)
+        self.base = {Tp: torch.arange(B, device=dev, dtype=torch.int32) * Tp for Tp in self.BUCKETS}
+        self.base_max = torch.arange(B, device=dev, dtype=torch.int64) * self.TMAX
+        self.graphs = {}
+        self.scale = 1.0 / math.sqrt(H // self.heads)
+        W = model._W
+        self.mtr, self.pvw = W["mtr"], W["pv"]
+
+    def _ln(self, x, W):
+        return K.layernorm_fwd(x, W.ln_g, W.ln_b, W.eps, save_stats=False)[0]
+
+    def _self_block(self, x, W, Tp, causal):
+        B, H = self.B, self.H
+        M = B * Tp
+        qkv = K.gemm(x, W.wqkv, M, 3 * H, H, bias=W.bqkv)
+        o = torch.empty(M, H, device=self.dev, dtype=torch.bfloat16)
+        K.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o, None, B, self.heads, Tp, Tp, self.kv_len_pv, causal, self.scale)
+        return self._ln(K.gemm(o, W.wo, M, H, H, bias=W.bo, residual=x), W)
+
+    def _ffn(self, x, F_, M):
+        act = K.gemm(x, F_.w1, M, self.I, self.H, bias=F_.b1, gelu=True)
+        return self._ln(K.gemm(act, F_.w2, M, self.H, self.I, bias=F_.b2, residual=x), F_)
+
+    def _step(self, Tp):
+        B, H = self.B, self.H
+        M = B * Tp
+        self.kv_len_pv.copy_(self.t_dev.expand(B))
+        x_in = self.prop_in[:, :Tp].contiguous()
+        emb = self.pb.emb
+        x = self._ln(K.embed_inputs_fwd(x_in, emb.pos, emb.type0), emb)
+        for lw in self.pb.layers:                                    # property encoder, bidirectional (d_smiles2pv.py:15)
+            x = self._self_block(x, lw.attn, Tp, False)
+            x = self._ffn(x, lw.ffn, M)
+        for j, lw in enumerate(self.tb.layers[self.fl:]):            # fusion layers, causal over the prefix (:17-24)
+            x = self._self_block(x, lw.attn, Tp, True)
+            C = lw.cross
+            q = K.gemm(x, C.wq, M, H, H, bias=C.bq)
+            kv = self.cross_kv[j]
+            o = torch.empty(M, H, device=self.dev, dtype=torch.bfloat16)
+            K.attn_fwd(q, kv[:, :H], kv[:, H:], o, None, B, self.heads, Tp, self.L, self.text_len, False, self.scale)
+            x = self._ln(K.gemm(o, C.wo, M, H, H, bias=C.bo, residual=x), C)
+            x = self._ffn(x, lw.ffn, M)
+        # regression head at the last position only (the reference applies it everywhere and reads [:, -1], :25-26)
+        idx = self.base[Tp] + self.t_dev - 1
+        last = K.gather_rows(x, idx, B)
+        mt = self.mtr
+        a = K.gemm(last, mt.w0, B, H, H, bias=mt.b0, gelu=True)
+        t = K.layernorm_fwd(a, mt.ln_g, mt.ln_b, mt.eps, save_stats=False)[0]
+        pred = t.float() @ mt.w3.view(-1) + mt.b3                   # [B]
+        tl = self.t_dev.long()
+        self.preds.index_copy_(1, tl - 1, pred[:, None])
+        nxt = (pred[:, None] * self.pvw.w[None, :] + self.pvw.b[None, :]).to(torch.bfloat16)     # property_embed, :49
+        self.prop_in.view(B * self.TMAX, H).index_copy_(0, self.base_max + tl, nxt)
+        self.t_dev.add_(1)
+
+    @torch.no_grad()
+    def generate(self, input_ids, attention_mask, n_prop=53):
+        from .xbert import raw_outputs
+        m = self.model
+        m.eval()
+        B, L, H = self.B, self.L, self.H
+        assert tuple(input_ids.shape) == (B, L) and n_prop <= 53
+        with raw_outputs():
+            text = m.text_encoder.bert(input_ids, attention_mask=attention_mask, return_dict=True, mode='text').last_hidden_state
+        t2 = text.reshape(B * L, H)
+        for j, lw in enumerate(self.tb.layers[self.fl:]):
+            K.gemm(t2, lw.cross.wkv, B * L, 2 * H, H, bias=lw.cross.bkv, out=self.cross_kv[j])
+        self.text_len.copy_(attention_mask.sum(1).to(torch.int32))
+        self.prop_in.zero_()
+        self.prop_in[:, 0] = m.property_cls.view(1, H).to(torch.bfloat16)
+        self.t_dev.fill_(1)
+        for s in range(n_prop):
+            Tp = next(b for b in self.BUCKETS if s + 1 <= b)
+            g = self.graphs.get(Tp)
+            if g is None:
+                snap = (self.prop_in.clone(), self.preds.clone(), self.t_dev.clone())
+                self._step(Tp)                                       # warm-up outside capture, then undo it
+                torch.cuda.synchronize()
+                self.prop_in.copy_(snap[0]); self.preds.copy_(snap[1]); self.t_dev.copy_(snap[2])
+                g = self.graphs[Tp] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step(Tp)
+            g.replay()
+        return self.preds[:, :n_prop].clone()
+
+
+_S2P = {}
+
+
+@torch.no_grad()
+def smiles2pv_fast(model, input_ids, attention_mask, n_prop=53):
+    """d_smiles2pv.py:41-52 through `Smiles2PvDecoder` (cached text-side cross K/V, graph-replayed steps)."""
+    key = (id(model), tuple(input_ids.shape))
+    dec = _S2P.get(key)
+    if dec is None or dec.model is not model:
+        dec = _S2P[key] = Smiles2PvDecoder(model, input_ids.shape[0], input_ids.shape[1])
+    dev = model.arena().device
+    return dec.generate(input_ids.to(dev), attention_mask.to(dev), n_prop)
