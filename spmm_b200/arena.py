@@ -119,6 +119,15 @@ class ParamArena:
     def grad(self, name, count=1):
         return self._slice(self.G, name, count=count)
 
+    def prefix_range(self, prefix):
+        """[lo, hi) of the arena occupied by the parameters whose name starts with `prefix` (e.g. one encoder layer):
+        contiguous by construction (named_parameters order); used to all-reduce a layer's gradients as soon as its last
+        backward contribution has been enqueued (trainer.GradOverlap)."""
+        spans = [(o, o + _pad(n)) for name, (o, n, _) in self.offset.items() if name.startswith(prefix)]
+        lo, hi = min(s[0] for s in spans), max(s[1] for s in spans)
+        assert all(name.startswith(prefix) for name, (o, n, _) in self.offset.items() if lo <= o < hi), prefix
+        return lo, hi
+
     # ------------------------------------------------------------------ maintenance
     def valid_for(self, model):
         name, p, _ = self._params[-1]
@@ -208,7 +217,8 @@ def bert_bundles(A, name, bert, momentum, anchor, head_prefix=None, is_property=
         layers.append(SimpleNamespace(
             attn=_attn_bundle(A, lp + ".attention", cfg, momentum, False),
             cross=_attn_bundle(A, lp + ".crossattention", cfg, momentum, True) if layer.has_cross_attention else None,
-            ffn=_ffn_bundle(A, lp, cfg, momentum)))
+            ffn=_ffn_bundle(A, lp, cfg, momentum),
+            grad_range=None if momentum else A.prefix_range(lp + ".")))
     head = None
     if head_prefix is not None:
         hp = head_prefix

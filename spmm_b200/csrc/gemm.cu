@@ -8,7 +8,8 @@
 // fwd (X.W^T), dgrad (dY.W) and wgrad (dY^T.X) all run without a transpose pass.
 //
 // Two kernels.  gemm2_bf16_kernel (below, "2-CTA kernel") carries the step: CTA pairs, 256 x 256 tiles,
-// cta_group::2 MMAs, 8 epilogue warps staging through shared memory into bulk tensor stores.  gemm_bf16_kernel<BN> is
+// cta_group::2 MMAs, 16 epilogue warps (packed-fp32 math on 16-column chunks) staging through shared memory into
+// bulk tensor stores, optional fused column sums (bias gradients).  gemm_bf16_kernel<BN> is
 // the 1-CTA variant kept for M <= 128, N <= 128 and ragged N (e.g. the 300-column LM head):
 //   persistent CTAs (one per SM), 256 threads:
 //   warp 0 lane 0 : TMA producer      (smem full/empty ring, kStages deep)
@@ -385,18 +386,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // own 128 rows of A and its own 128 columns of B (32 KB per 64-deep k-block instead of 48 KB), the leader CTA issues
 // UMMA M=256 that reads both CTAs' shared memory, and each CTA's TMEM receives its 128 output rows.
 //
-// Epilogue (8 warps per CTA, two per TMEM lane quadrant): accumulators go TMEM -> registers -> fused math ->
+// Epilogue (16 warps per CTA, four per TMEM lane quadrant): accumulators go TMEM -> registers -> fused math ->
 // SWIZZLE_128B staging tile in shared memory -> ONE bulk tensor store (or f32 reduce-add) per 128x64 box, and the
 // residual / dGELU side operand arrives in the same staging tile by TMA while the mainloop runs.  A thread owns one
 // output row, so direct global stores were 16-byte pieces on 32 different lines per instruction: the phase trace
-// (tools/gemm_trace.py) showed 4-11 us of epilogue per tile against 5 us of mainloop at K=768.
+// (tools/gemm_trace.py) showed 4-11 us of epilogue per tile against 5 us of mainloop at K=768.  The per-element math
+// runs on packed fp32 pairs (FFMA2) and, being latency-bound, on four warps per scheduler.
 constexpr int BN2 = 256;
 constexpr int B2_STAGE_BYTES = (BN2 / 2) * BK * 2;               // this CTA's half of the B tile
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;     // 32 KB
 constexpr int kStages2 = 5;
 constexpr int STG_BOX_BYTES = 128 * 128;                         // [128 rows][128 B], 16-byte units XOR (row & 7)
 constexpr int STG_BYTES = 4 * STG_BOX_BYTES;                     // 64 KB: 128 x 256 bf16, or 128 x 128 f32
-constexpr int kThreads2 = 384;
+constexpr int kThreads2 = 128 + 16 * 32;   // TMA / MMA / TMEM-alloc / side-loader warps + 16 epilogue warps
 constexpr int SMEM2_BYTES = kStages2 * STAGE2_BYTES + STG_BYTES + 1024 /*align*/ + 512 /*barriers*/ + BN2 * 4 /*bias*/;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -455,120 +457,54 @@ struct Gemm2Maps {
   CUtensorMap a, b, c, side, pre;   // side: residual or dGELU factor (bf16, same shape as C); pre: 2nd bf16 output
 };
 
-// One 32-column chunk of this thread's row: fused math on v[32], side operand / result through the staging tile.
+// ---- epilogue chunk math (2-CTA kernel).  A thread owns one output row; a chunk is C = 16 consecutive columns of it.
 // Staging address of 16-byte unit u of row r in a box: box + r*128 + ((u ^ (r & 7)) << 4).
-__device__ __forceinline__ void epi2_chunk(const GemmParams& p, float (&v)[32], const float* s_bias_chunk, const int row_g,
-                                           const int col0, const uint32_t drop_key, uint8_t* out_row, uint8_t* pre_row,
-                                           const int u0, const int sw, const bool has_side, const uint4 (&side)[4]) {
-  const bool out_f32 = p.flags & SPMM_GEMM_OUT_F32;
-  if (p.bias != nullptr) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 b = *reinterpret_cast<const float4*>(s_bias_chunk + 4 * i);   // smem broadcast
-      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-    }
-  }
-  if (pre_row != nullptr && (p.flags & SPMM_GEMM_DGELU_STORED) && (p.flags & SPMM_GEMM_GELU)) {
-    // 2nd output = gelu'(pre): backward then only multiplies.  One erf evaluation gives both gelu and gelu'.
-    float gr[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_and_grad(v[j], &gr[j]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 o;
-      o.x = pack_bf16x2(gr[8 * i], gr[8 * i + 1]); o.y = pack_bf16x2(gr[8 * i + 2], gr[8 * i + 3]);
-      o.z = pack_bf16x2(gr[8 * i + 4], gr[8 * i + 5]); o.w = pack_bf16x2(gr[8 * i + 6], gr[8 * i + 7]);
-      *reinterpret_cast<uint4*>(pre_row + (((u0 + i) ^ sw) << 4)) = o;
-    }
-  } else {
-  if (pre_row != nullptr) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 o;
-      o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      *reinterpret_cast<uint4*>(pre_row + (((u0 + i) ^ sw) << 4)) = o;
-    }
-  }
-  if (p.flags & SPMM_GEMM_GELU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  }
-  }
-  if (p.drop_thresh16 != 0) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {   // element index row*N + col is even here (N % 8 == 0, col0 % 32 == 0)
-      const uint32_t e = (uint32_t)row_g * (uint32_t)p.N + (uint32_t)(col0 + j);
-      drop_pair(drop_key, e, p.drop_thresh16, p.drop_inv_keep, v[j], v[j + 1]);
-    }
-  }
-  if (has_side) {   // bf16 side operand (residual / dGELU factor), prefetched from global memory into registers
-    const bool do_dgelu = p.flags & SPMM_GEMM_DGELU, stored = p.flags & SPMM_GEMM_DGELU_STORED;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 sv = side[i];
-      float s[8];
-      unpack_bf16x2(sv.x, s[0], s[1]); unpack_bf16x2(sv.y, s[2], s[3]);
-      unpack_bf16x2(sv.z, s[4], s[5]); unpack_bf16x2(sv.w, s[6], s[7]);
-      if (do_dgelu && stored) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[8 * i + j] *= s[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[8 * i + j] = do_dgelu ? v[8 * i + j] * dgelu_erf(s[j]) : v[8 * i + j] + s[j];
-      }
-    }
-  }
-  if (out_f32) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      *reinterpret_cast<float4*>(out_row + ((i ^ sw) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 o;
-      o.x = pack_bf16x2(v[8 * i], v[8 * i + 1]); o.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      o.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      *reinterpret_cast<uint4*>(out_row + (((u0 + i) ^ sw) << 4)) = o;
-    }
-  }
-}
-
-// ---- fast epilogue paths on packed fp32 pairs (FFMA2): the three shapes that carry the step ------------------------
 enum { EPI_GENERIC = 0, EPI_GELU_GRAD = 1, EPI_DGELU_MUL = 2, EPI_LINEAR = 3 };
+constexpr int EC = 16;              // columns per epilogue chunk
+constexpr int ENP = EC / 2;         // packed fp32 pairs per chunk
+constexpr int ESU = EC / 8;         // 16-byte units of a bf16 chunk
 
-__device__ __forceinline__ void stage_units(uint8_t* row, const int u0, const int sw, const f32x2 (&v)[16]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void stage_units(uint8_t* row, const int u0, const int sw, const f32x2 (&v)[ENP]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < ESU; ++i) {
     uint4 o;
     o.x = f32x2_to_bf16x2(v[4 * i]); o.y = f32x2_to_bf16x2(v[4 * i + 1]);
     o.z = f32x2_to_bf16x2(v[4 * i + 2]); o.w = f32x2_to_bf16x2(v[4 * i + 3]);
     *reinterpret_cast<uint4*>(row + (((u0 + i) ^ sw) << 4)) = o;
   }
 }
-__device__ __forceinline__ void add_bias2(f32x2 (&v)[16], const float* s_bias_chunk) {
+__device__ __forceinline__ void add_bias2(f32x2 (&v)[ENP], const float* s_bias_chunk) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < EC / 4; ++i) {
     const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(s_bias_chunk + 4 * i);   // smem broadcast, two pairs
     v[2 * i] = add2(v[2 * i], b.x);
     v[2 * i + 1] = add2(v[2 * i + 1], b.y);
   }
 }
 // FFN-up forward (reference xbert.py:434-437): act = gelu(acc + bias) -> out box, gelu'(acc + bias) -> 2nd output box
-__device__ __forceinline__ void epi2_gelu_grad(f32x2 (&v)[16], const float* s_bias_chunk, uint8_t* out_row, uint8_t* pre_row,
+__device__ __forceinline__ void epi2_gelu_grad(f32x2 (&v)[ENP], const float* s_bias_chunk, uint8_t* out_row, uint8_t* pre_row,
                                                const int u0, const int sw) {
   add_bias2(v, s_bias_chunk);
-  f32x2 gr[16];
+  f32x2 gr[ENP];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) gelu_and_grad2(v[j], v[j], gr[j]);
+  for (int j = 0; j < ENP; ++j) gelu_and_grad2(v[j], v[j], gr[j]);
   stage_units(pre_row, u0, sw, gr);
   stage_units(out_row, u0, sw, v);
 }
 // FFN backward: d pre = (dY . W2) * gelu'(pre), the factor stored by the forward
-__device__ __forceinline__ void epi2_dgelu_mul(f32x2 (&v)[16], const uint4 (&side)[4], uint8_t* out_row, const int u0,
+__device__ __forceinline__ void epi2_dgelu_mul(f32x2 (&v)[ENP], const uint4 (&side)[ESU], uint8_t* out_row, const int u0,
                                                const int sw) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < ESU; ++i) {
     v[4 * i] = mul2(v[4 * i], bf16x2_to_f32x2(side[i].x));
     v[4 * i + 1] = mul2(v[4 * i + 1], bf16x2_to_f32x2(side[i].y));
     v[4 * i + 2] = mul2(v[4 * i + 2], bf16x2_to_f32x2(side[i].z));
@@ -577,14 +513,14 @@ __device__ __forceinline__ void epi2_dgelu_mul(f32x2 (&v)[16], const uint4 (&sid
   stage_units(out_row, u0, sw, v);
 }
 // dense (+ bias) (+ inverted dropout) (+ residual): BertSelfOutput / BertOutput (xbert.py:369-373, 447-451), QKV, dgrads
-__device__ __forceinline__ void epi2_linear(const GemmParams& p, f32x2 (&v)[16], const float* s_bias_chunk, const int row_g,
+__device__ __forceinline__ void epi2_linear(const GemmParams& p, f32x2 (&v)[ENP], const float* s_bias_chunk, const int row_g,
                                             const int col0, const uint32_t drop_key, const bool has_res,
-                                            const uint4 (&side)[4], uint8_t* out_row, const int u0, const int sw) {
+                                            const uint4 (&side)[ESU], uint8_t* out_row, const int u0, const int sw) {
   if (p.bias != nullptr) add_bias2(v, s_bias_chunk);
   if (p.drop_thresh16 != 0) {
-    const uint32_t e0 = (uint32_t)row_g * (uint32_t)p.N + (uint32_t)col0;   // even (N % 8 == 0, col0 % 32 == 0)
+    const uint32_t e0 = (uint32_t)row_g * (uint32_t)p.N + (uint32_t)col0;   // even (N % 8 == 0, col0 % 16 == 0)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < ENP; ++j) {
       const uint32_t hbits = drop_bits2(drop_key, e0 + 2 * j);
       const float m0 = ((hbits & 0xFFFFu) >= p.drop_thresh16) ? p.drop_inv_keep : 0.f;
       const float m1 = ((hbits >> 16) >= p.drop_thresh16) ? p.drop_inv_keep : 0.f;
@@ -593,7 +529,7 @@ __device__ __forceinline__ void epi2_linear(const GemmParams& p, f32x2 (&v)[16],
   }
   if (has_res) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < ESU; ++i) {
       v[4 * i] = add2(v[4 * i], bf16x2_to_f32x2(side[i].x));
       v[4 * i + 1] = add2(v[4 * i + 1], bf16x2_to_f32x2(side[i].y));
       v[4 * i + 2] = add2(v[4 * i + 2], bf16x2_to_f32x2(side[i].z));
@@ -601,6 +537,67 @@ __device__ __forceinline__ void epi2_linear(const GemmParams& p, f32x2 (&v)[16],
     }
   }
   stage_units(out_row, u0, sw, v);
+}
+// every other flag combination (fp32 outputs: wgrad accumulate / split-K; un-stored GELU variants; alpha != 1)
+__device__ __forceinline__ void epi2_generic(const GemmParams& p, float (&v)[EC], const float* s_bias_chunk, const int row_g,
+                                             const int col0, const uint32_t drop_key, uint8_t* out_row, uint8_t* pre_row,
+                                             const int u0, const int sw, const bool has_side, const uint4 (&side)[ESU]) {
+  const bool out_f32 = p.flags & SPMM_GEMM_OUT_F32;
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < EC / 4; ++i) {
+      const float4 b = *reinterpret_cast<const float4*>(s_bias_chunk + 4 * i);   // smem broadcast
+      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+  }
+  auto stage_bf16 = [&](uint8_t* row, const float (&x)[EC]) {
+#pragma unroll
+    for (int i = 0; i < ESU; ++i) {
+      uint4 o;
+      o.x = pack_bf16x2(x[8 * i], x[8 * i + 1]); o.y = pack_bf16x2(x[8 * i + 2], x[8 * i + 3]);
+      o.z = pack_bf16x2(x[8 * i + 4], x[8 * i + 5]); o.w = pack_bf16x2(x[8 * i + 6], x[8 * i + 7]);
+      *reinterpret_cast<uint4*>(row + (((u0 + i) ^ sw) << 4)) = o;
+    }
+  };
+  if (pre_row != nullptr && (p.flags & SPMM_GEMM_DGELU_STORED) && (p.flags & SPMM_GEMM_GELU)) {
+    float gr[EC];   // 2nd output = gelu'(pre): one erf evaluation gives both gelu and gelu'
+#pragma unroll
+    for (int j = 0; j < EC; ++j) v[j] = gelu_and_grad(v[j], &gr[j]);
+    stage_bf16(pre_row, gr);
+  } else {
+    if (pre_row != nullptr) stage_bf16(pre_row, v);
+    if (p.flags & SPMM_GEMM_GELU) {
+#pragma unroll
+      for (int j = 0; j < EC; ++j) v[j] = gelu_erf(v[j]);
+    }
+  }
+  if (p.drop_thresh16 != 0) {
+#pragma unroll
+    for (int j = 0; j < EC; j += 2) {   // element index row*N + col is even here (N % 8 == 0, col0 % 16 == 0)
+      const uint32_t e = (uint32_t)row_g * (uint32_t)p.N + (uint32_t)(col0 + j);
+      drop_pair(drop_key, e, p.drop_thresh16, p.drop_inv_keep, v[j], v[j + 1]);
+    }
+  }
+  if (has_side) {   // bf16 side operand (residual / dGELU factor)
+    const bool do_dgelu = p.flags & SPMM_GEMM_DGELU, stored = p.flags & SPMM_GEMM_DGELU_STORED;
+#pragma unroll
+    for (int i = 0; i < ESU; ++i) {
+      const uint4 sv = side[i];
+      float s[8];
+      unpack_bf16x2(sv.x, s[0], s[1]); unpack_bf16x2(sv.y, s[2], s[3]);
+      unpack_bf16x2(sv.z, s[4], s[5]); unpack_bf16x2(sv.w, s[6], s[7]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[8 * i + j] = do_dgelu ? v[8 * i + j] * (stored ? s[j] : dgelu_erf(s[j])) : v[8 * i + j] + s[j];
+    }
+  }
+  if (out_f32) {    // 16 fp32 = 4 units
+#pragma unroll
+    for (int i = 0; i < EC / 4; ++i)
+      *reinterpret_cast<float4*>(out_row + (((u0 + i) ^ sw) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    stage_bf16(out_row, v);
+  }
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
@@ -645,10 +642,10 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);    // multicast commit
-      mbar_init(&tempty_bar[s], 16);  // leader's copy: 8 epilogue warps x 2 CTAs
+      mbar_init(&tempty_bar[s], 32);  // leader's copy: 16 epilogue warps x 2 CTAs
     }
     mbar_init(side_full, 1);
-    mbar_init(stage_free, 2);
+    mbar_init(stage_free, 4);      // one arrive per column group
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -753,114 +750,121 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       ph ^= 1;
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (both CTAs: own 128 rows x 256 columns) =====================
-    const int q = warp & 3;             // TMEM lane quadrant this warp may read
-    const int h = (warp - 4) >> 2;      // column half: columns [128h, 128h + 128) of the tile
-    const int bar_id = 1 + h;
-    const bool elected = (warp == 4 + 4 * h) && lane == 0;
+    // ===================== epilogue (both CTAs: own 128 rows x 256 columns), 16 warps =====================
+    // Warp w = 4 + 4g + q reads TMEM lane quadrant q (rows 32q .. 32q+31 of this CTA's tile) and owns column group g
+    // (64 columns).  The epilogues are latency-bound (the phase traces showed ~5 cycles per instruction per warp with 8
+    // warps = 2 per scheduler), so 4 warps per scheduler on 16-column chunks is what buys throughput; 96 registers.
+    //   single bf16 output : group g -> staging box g (64 columns), its own bulk store, barrier over the group
+    //   fp32 output        : two 64-column sub-phases per column half; group (h, j) -> box 2h+j (32 fp32 columns), own store
+    //   2nd bf16 output    : two 64-column sub-phases per half; both groups of the half fill [pre box 2h | act box 2h+1],
+    //                        barrier over the half, one thread stores both boxes
+    const int q = warp & 3;
+    const int g = (warp - 4) >> 2, h = g >> 1, j = g & 1;
     const int r = q * 32 + lane;        // row within this CTA's 128-row tile
     const int sw = r & 7;
+    const bool two_phase = out_f32 || has_pre;
+    const bool half_sync = has_pre && !out_f32;
+    const int gbar = 1 + g, hbar = 5 + h, allbar = 7;
+    const bool g_elected = q == 0 && lane == 0;
+    const bool st_elected = half_sync ? (g_elected && j == 0) : g_elected;   // the thread that issues this scope's stores
     const uint32_t drop_key = p.drop_thresh16 ? fold_seed(salted(p.drop_seed, p.salt)) : 0u;
-    // 64-column sub-phases when a chunk needs two boxes' worth of staging (f32 output, or a 2nd bf16 output).
-    // (Tried: four 32-column sub-phases through a 2-deep ring of [128 rows][64 B] half-boxes so that the store drain of
-    // one sub-phase overlaps the next - the narrower bulk stores made the FFN-up GEMM slower, 48 vs 44 us.)
-    const int nsub = (out_f32 || has_pre) ? 2 : 1;
-    // fast path selection (warp-uniform, once per kernel): packed-pair math for the shapes that carry the step
-    int mode = EPI_GENERIC;
+    int mode = EPI_GENERIC;   // fast path selection (warp-uniform, once per kernel)
     if (p.alpha == 1.f && !out_f32) {
-      const bool g = p.flags & SPMM_GEMM_GELU, dg = p.flags & SPMM_GEMM_DGELU, st = p.flags & SPMM_GEMM_DGELU_STORED;
-      if (g && st && has_pre && !has_side && p.drop_thresh16 == 0 && p.bias != nullptr) mode = EPI_GELU_GRAD;
-      else if (dg && st && !g && !has_pre && p.bias == nullptr && p.drop_thresh16 == 0) mode = EPI_DGELU_MUL;
-      else if (!g && !dg && !has_pre) mode = EPI_LINEAR;
+      const bool ge = p.flags & SPMM_GEMM_GELU, dg = p.flags & SPMM_GEMM_DGELU, st = p.flags & SPMM_GEMM_DGELU_STORED;
+      if (ge && st && has_pre && !has_side && p.drop_thresh16 == 0 && p.bias != nullptr) mode = EPI_GELU_GRAD;
+      else if (dg && st && !ge && !has_pre && p.bias == nullptr && p.drop_thresh16 == 0) mode = EPI_DGELU_MUL;
+      else if (!ge && !dg && !has_pre) mode = EPI_LINEAR;
     }
     // The bf16 side operand (residual, or the stored gelu' factor) arrives by TMA in the output staging tile
     // (side_tma: single bf16 output) and is replaced in place by the result; with a 2nd output the staging tile has no
-    // room for it and the thread that owns the row reads it from global memory one 32-column chunk (64 B) ahead.
+    // room for it and the thread that owns the row reads it from global memory one chunk ahead.
     const __nv_bfloat16* side = (p.flags & SPMM_GEMM_DGELU) ? p.aux : p.residual;
     const int lds = (p.flags & SPMM_GEMM_DGELU) ? p.ldaux : p.ldr;
     const bool side_tma = has_side && p.side_tma;
     const bool side_reg = has_side && !p.side_tma;
+    const int nsub = two_phase ? 2 : 1, nch = two_phase ? 2 : 4;
     int acc = 0;
     uint32_t acc_phase = 0, side_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int mn = tile % num_mn;
       const int m0 = (mn % num_m) * 2 * BM + (int)rank * BM, n0 = (mn / num_m) * BN2;
-      const int nh0 = n0 + 128 * h;     // first column of this half
       const bool row_ok = m0 + r < p.M;
       const __nv_bfloat16* side_row = has_side ? side + (size_t)(m0 + r) * lds : nullptr;
-      uint4 side_next[4];
-      auto load_side = [&](int col, uint4(&dst)[4]) {
+      // tile column of chunk c of sub-phase `sub`
+      auto chunk_col = [&](int sub, int c) { return two_phase ? 128 * h + 64 * sub + 32 * j + EC * c : 64 * g + EC * c; };
+      uint4 side_next[ESU];
+      auto load_side = [&](int col, uint4(&dst)[ESU]) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < ESU; ++i) {
           if (side_reg && row_ok && col + 8 * i + 8 <= p.N) dst[i] = __ldg(reinterpret_cast<const uint4*>(side_row + col + 8 * i));
           else dst[i] = make_uint4(0u, 0u, 0u, 0u);
         }
       };
-      load_side(nh0, side_next);        // in flight while the MMAs of this tile are still running
-      // staging boxes of this half are free (previous stores have read them) and the previous bias reads are done
-      if (elected) bulk_wait_read0();
-      bar_sync_named(bar_id, 128);
+      load_side(n0 + chunk_col(0, 0), side_next);   // in flight while the MMAs of this tile are still running
+      // staging free (previous stores have read it), previous bias reads and column sums done
+      if (st_elected) bulk_wait_read0();
+      bar_sync_named(allbar, 32 * 16);
       if (p.bias != nullptr) {
-        const int t = threadIdx.x - 128 - 128 * h;
-        s_bias[128 * h + t] = (nh0 + t < p.N) ? __ldg(p.bias + nh0 + t) : 0.f;
-        bar_sync_named(bar_id, 128);
+        const int t = threadIdx.x - 128;
+        if (t < BN2) s_bias[t] = (n0 + t < p.N) ? __ldg(p.bias + n0 + t) : 0.f;
+        bar_sync_named(allbar, 32 * 16);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       if (side_tma) mbar_wait(side_full, side_phase);
       tc_fence_after();
       if (warp == 4 && lane == 0 && tile == pair) trace_mark(p, 5);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN2 + 128 * h;
-      // TMEM reads are software-pipelined across chunks and sub-phases: the load of chunk c+1 is in flight while chunk
-      // c is processed
-      uint32_t rr[32];
-      if (nh0 < p.N) tmem_ld32(taddr, rr);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN2;
+      // TMEM reads are software-pipelined across chunks and sub-phases
+      uint32_t rr[EC];
+      if (n0 + chunk_col(0, 0) < p.N) tmem_ld16(taddr + chunk_col(0, 0), rr);
       for (int sub = 0; sub < nsub; ++sub) {
         if (sub > 0) {
-          if (elected) bulk_wait_read0();
-          bar_sync_named(bar_id, 128);
+          if (st_elected) bulk_wait_read0();
+          if (half_sync) bar_sync_named(hbar, 256); else bar_sync_named(gbar, 128);
           if (warp == 4 && lane == 0 && tile == pair) trace_mark(p, 14);
         }
-        const int nchunk = 4 / nsub;
 #pragma unroll 1
-        for (int cc = 0; cc < nchunk; ++cc) {
-          const int c = sub * nchunk + cc;            // chunk within the half: columns nh0 + 32c
-          const int col0 = nh0 + 32 * c;
+        for (int c = 0; c < nch; ++c) {
+          const int ct = chunk_col(sub, c);
+          const int col0 = n0 + ct;
           if (col0 >= p.N) break;                     // warp-uniform
-          uint4 side_cur[4];
+          uint4 side_cur[ESU];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) side_cur[i] = side_next[i];
-          if (side_reg && c + 1 < 4) load_side(col0 + 32, side_next);
+          for (int i = 0; i < ESU; ++i) side_cur[i] = side_next[i];
+          // next chunk of this thread (possibly in the next sub-phase)
+          const bool last = (c + 1 == nch) && (sub + 1 == nsub);
+          const int ct_next = last ? 0 : (c + 1 < nch ? chunk_col(sub, c + 1) : chunk_col(sub + 1, 0));
+          const bool more = !last && n0 + ct_next < p.N;
+          if (side_reg && more) load_side(n0 + ct_next, side_next);
           tmem_ld_wait();
-          // staging placement: bf16 -> box 2h + (c >> 1), units 4*(c & 1)..+3; pre mode -> act box 2h+1 / pre box 2h,
-          // units 4*cc..+3; f32 -> box 2h + cc, units 0..7
+          // staging placement (16-byte units within the row of a [128 rows][128 B] box)
           uint8_t* out_row;
           uint8_t* pre_row = nullptr;
           int u0;
-          if (out_f32) { out_row = staging + (2 * h + cc) * STG_BOX_BYTES + r * 128; u0 = 0; }
+          if (out_f32) { out_row = staging + (2 * h + j) * STG_BOX_BYTES + r * 128; u0 = 4 * c; }
           else if (has_pre) {
             out_row = staging + (2 * h + 1) * STG_BOX_BYTES + r * 128;
             pre_row = staging + (2 * h) * STG_BOX_BYTES + r * 128;
-            u0 = 4 * cc;
-          } else { out_row = staging + (2 * h + (c >> 1)) * STG_BOX_BYTES + r * 128; u0 = 4 * (c & 1); }
-          const bool more = c + 1 < 4 && col0 + 32 < p.N;
+            u0 = 4 * j + ESU * c;
+          } else { out_row = staging + g * STG_BOX_BYTES + r * 128; u0 = ESU * c; }
           if (side_tma) {   // the side operand sits where the result goes
 #pragma unroll
-            for (int i = 0; i < 4; ++i) side_cur[i] = *reinterpret_cast<const uint4*>(out_row + (((u0 + i) ^ sw) << 4));
+            for (int i = 0; i < ESU; ++i) side_cur[i] = *reinterpret_cast<const uint4*>(out_row + (((u0 + i) ^ sw) << 4));
           }
           if (mode != EPI_GENERIC) {
-            f32x2 v2[16];
+            f32x2 v2[ENP];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v2[j] = pk2(__uint_as_float(rr[2 * j]), __uint_as_float(rr[2 * j + 1]));
-            if (more) tmem_ld32(taddr + (c + 1) * 32, rr);
-            if (mode == EPI_GELU_GRAD) epi2_gelu_grad(v2, s_bias + 128 * h + 32 * c, out_row, pre_row, u0, sw);
+            for (int i = 0; i < ENP; ++i) v2[i] = pk2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
+            if (more) tmem_ld16(taddr + ct_next, rr);
+            if (mode == EPI_GELU_GRAD) epi2_gelu_grad(v2, s_bias + ct, out_row, pre_row, u0, sw);
             else if (mode == EPI_DGELU_MUL) epi2_dgelu_mul(v2, side_cur, out_row, u0, sw);
-            else epi2_linear(p, v2, s_bias + 128 * h + 32 * c, m0 + r, col0, drop_key, has_side, side_cur, out_row, u0, sw);
+            else epi2_linear(p, v2, s_bias + ct, m0 + r, col0, drop_key, has_side, side_cur, out_row, u0, sw);
           } else {
-            float v[32];
+            float v[EC];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
-            if (more) tmem_ld32(taddr + (c + 1) * 32, rr);
-            epi2_chunk(p, v, s_bias + 128 * h + 32 * c, m0 + r, col0, drop_key, out_row, pre_row, u0, sw, has_side, side_cur);
+            for (int i = 0; i < EC; ++i) v[i] = __uint_as_float(rr[i]) * p.alpha;
+            if (more) tmem_ld16(taddr + ct_next, rr);
+            epi2_generic(p, v, s_bias + ct, m0 + r, col0, drop_key, out_row, pre_row, u0, sw, has_side, side_cur);
           }
         }
         if (sub == nsub - 1) {            // accumulator fully read: hand the TMEM buffer back to the MMA issuer
@@ -870,46 +874,43 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
         }
         if (warp == 4 && lane == 0 && tile == pair) trace_mark(p, sub == 0 ? 12 : 15);
         fence_proxy_async();
-        bar_sync_named(bar_id, 128);
+        if (half_sync) bar_sync_named(hbar, 256); else bar_sync_named(gbar, 128);
         if (warp == 4 && lane == 0 && tile == pair && sub == 0) trace_mark(p, 13);
-        if (elected) {
-          const int cs = nh0 + sub * 64;   // first column of this sub-phase (nsub == 2)
+        if (st_elected) {
           if (out_f32) {
-#pragma unroll
-            for (int b = 0; b < 2; ++b)
-              if (cs + 32 * b < p.N) {
-                if ((p.flags & SPMM_GEMM_ACCUMULATE) || p.splits > 1)
-                  tma_reduce_add_2d(&maps.c, staging + (2 * h + b) * STG_BOX_BYTES, cs + 32 * b, m0);
-                else
-                  tma_store_2d(&maps.c, staging + (2 * h + b) * STG_BOX_BYTES, cs + 32 * b, m0);
-              }
+            const int cs = n0 + 128 * h + 64 * sub + 32 * j;       // this group's 32 fp32 columns
+            if (cs < p.N) {
+              if ((p.flags & SPMM_GEMM_ACCUMULATE) || p.splits > 1)
+                tma_reduce_add_2d(&maps.c, staging + (2 * h + j) * STG_BOX_BYTES, cs, m0);
+              else
+                tma_store_2d(&maps.c, staging + (2 * h + j) * STG_BOX_BYTES, cs, m0);
+            }
           } else if (has_pre) {
+            const int cs = n0 + 128 * h + 64 * sub;                 // this half's 64 columns of the sub-phase
             if (cs < p.N) {
               tma_store_2d(&maps.pre, staging + (2 * h) * STG_BOX_BYTES, cs, m0);
               tma_store_2d(&maps.c, staging + (2 * h + 1) * STG_BOX_BYTES, cs, m0);
             }
           } else {
-#pragma unroll
-            for (int b = 0; b < 2; ++b)
-              if (nh0 + 64 * b < p.N) tma_store_2d(&maps.c, staging + (2 * h + b) * STG_BOX_BYTES, nh0 + 64 * b, m0);
+            if (n0 + 64 * g < p.N) tma_store_2d(&maps.c, staging + g * STG_BOX_BYTES, n0 + 64 * g, m0);
           }
           bulk_commit();
         }
-        if (p.colsum != nullptr && !out_f32 && !has_pre) {
-          // Column sums of this CTA's 128 x 128 half-tile from the staged bf16 values (what a separate pass over the
-          // stored tensor would read), while the bulk store drains: thread = (column pair, row half), 64 rows each,
-          // rows >= M skipped.  Addresses: row 64rh + 8a + b sits at base + a*1024 + b*128 + ((u ^ b) << 4).
-          const int t = threadIdx.x - 128 - 128 * h;
-          const int cp = t & 63, rh = t >> 6;                  // columns nh0 + 2cp, +1; rows 64rh .. 64rh + 63
-          const int u = (cp & 31) >> 2;
-          const uint8_t* base = staging + (2 * h + (cp >> 5)) * STG_BOX_BYTES + (64 * rh) * 128 + (cp & 3) * 4;
-          const int rmax = p.M - (m0 + 64 * rh);               // rows of this CTA's tile that exist (may be <= 0)
+        if (p.colsum != nullptr && !two_phase) {
+          // Column sums of this group's 128 x 64 box from the staged bf16 values (what a separate pass over the stored
+          // tensor would read), while the bulk store drains: thread = (column pair, row quarter), 32 rows each, rows >= M
+          // skipped.  Row 32rq + 8a + b of the box sits at base + a*1024 + b*128 + ((u ^ b) << 4).
+          const int t = threadIdx.x - 128 - 128 * g;
+          const int cp = t & 31, rq = t >> 5;
+          const int u = cp >> 2;
+          const uint8_t* base = staging + g * STG_BOX_BYTES + (32 * rq) * 128 + (cp & 3) * 4;
+          const int rmax = p.M - (m0 + 32 * rq);               // rows of this quarter that exist (may be <= 0)
           f32x2 acc_a = 0ull, acc_b = 0ull;
 #pragma unroll
           for (int b = 0; b < 8; ++b) {
             const uint8_t* pb = base + b * 128 + ((u ^ b) << 4);
 #pragma unroll
-            for (int a = 0; a < 8; a += 2) {
+            for (int a = 0; a < 4; a += 2) {
               const uint32_t w0 = *reinterpret_cast<const uint32_t*>(pb + a * 1024);
               const uint32_t w1 = *reinterpret_cast<const uint32_t*>(pb + (a + 1) * 1024);
               if (8 * a + b < rmax) acc_a = add2(acc_a, bf16x2_to_f32x2(w0));
@@ -918,15 +919,15 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
           }
           float s0, s1;
           upk2(add2(acc_a, acc_b), s0, s1);
-          const int col = nh0 + 2 * cp;
+          const int col = n0 + 64 * g + 2 * cp;
           if (col < p.N) {
             atomicAdd(p.colsum + col, s0);
             atomicAdd(p.colsum + col + 1, s1);
           }
-          if (side_tma) bar_sync_named(bar_id, 128);   // every thread has left the staging tile before it is refilled
+          if (side_tma) bar_sync_named(gbar, 128);   // every thread has left the box before the side loader refills it
         }
       }
-      if (side_tma && elected) {   // let the side loader refill the staging tile for the next tile
+      if (side_tma && g_elected) {   // let the side loader refill this group's box for the next tile
         bulk_wait_read0();
         mbar_arrive(stage_free);
       }
@@ -935,7 +936,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (elected) bulk_wait_read0();  // the staging tile must outlive the bulk stores' reads (writes drain with the grid)
+    if (g_elected) bulk_wait_read0();  // the staging tile must outlive the bulk stores' reads (writes drain with the grid)
   }
   if (threadIdx.x == 0) trace_mark(p, 7);
   tc_fence_before();

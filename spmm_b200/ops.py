@@ -83,6 +83,27 @@ def _wgrad(dy, x, gw, n_out, k_in, m_tokens):
         K.gemm(dy, x, n_out, k_in, m_tokens, a_mn=True, b_mn=True, out=gw, out_f32=True, accumulate=True)
 
 
+# --------------------------------------------------------------------------------------------- backward markers
+class _GradReady(torch.autograd.Function):
+    """Identity whose backward runs `callback()` first.  Placed on the INPUT of a layer in the first forward pass that
+    uses the layer's weights: autograd runs nodes in reverse creation order, so when this backward fires every kernel
+    that adds to those weights' gradients (in this and all later passes) has been enqueued."""
+
+    @staticmethod
+    def forward(ctx, x, callback):
+        ctx.callback = callback
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.callback()
+        return g, None
+
+
+def grad_ready(x, callback):
+    return _GradReady.apply(x, callback)
+
+
 # --------------------------------------------------------------------------------------------- attention block
 class _AttnBlock(torch.autograd.Function):
     @staticmethod

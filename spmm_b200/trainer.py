@@ -12,18 +12,92 @@ def world_size():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
+class GradOverlap:
+    """Gradient all-reduce overlapped with backward (what DDPStrategy gives the reference, SPMM_pretrain.py:35-36).
+
+    The gradient arena is one flat buffer; an encoder layer owns a contiguous range of it.  Every layer is used by
+    several passes of SPMM.forward, and autograd runs backward in reverse creation order, so a layer's gradients are
+    final once the backward of the FIRST forward pass that used it has been enqueued.  That pass carries a marker on
+    the layer's input (xbert.py); the marker's backward records an event, and a communication stream that waits on it
+    all-reduces the layer's range while the main stream continues with the layers below.  `finish()` joins the
+    streams and reduces whatever no marker covered (embeddings, heads - a few MB).  Works eagerly and under CUDA-graph
+    capture (fork / join through events).  `check=True` (single rank, tests): instead of communicating, snapshot the
+    range at marker time and verify at the end that nothing was added to it afterwards."""
+
+    def __init__(self, arena, check=False):
+        self.A, self.check = arena, check
+        self.stream = None if check else torch.cuda.Stream(device=arena.device)
+        self.done, self.claimed, self.snaps = [], set(), []
+
+    def begin(self):
+        self.done, self.claimed, self.snaps = [], set(), []
+
+    def claim(self, rng):
+        if rng in self.claimed:
+            return False
+        self.claimed.add(rng)
+        return True
+
+    def callback(self, rng):
+        return lambda: self.ready(*rng)
+
+    def ready(self, lo, hi):
+        G = self.A.G
+        if self.check:
+            self.snaps.append((lo, hi, G[lo:hi].clone()))
+        else:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.stream.wait_event(ev)
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(G[lo:hi], op=dist.ReduceOp.SUM)
+        self.done.append((lo, hi))
+
+    def finish(self):
+        A = self.A
+        if self.check:
+            bad = [(lo, hi) for lo, hi, snap in self.snaps if not torch.equal(snap, A.G[lo:hi])]
+            assert not bad, "gradient ranges modified after their all-reduce was issued: %s" % bad[:4]
+            return len(self.snaps)
+        torch.cuda.current_stream().wait_stream(self.stream)
+        pos = A.adam_start
+        for lo, hi in sorted(self.done) + [(A.n_total, A.n_total)]:      # the complement of the ranges already reduced
+            if lo > pos:
+                dist.all_reduce(A.G[pos:lo], op=dist.ReduceOp.SUM)
+            pos = max(pos, hi)
+        return len(self.done)
+
+
+def _overlap_enabled():
+    import os
+    return os.environ.get("SPMM_DDP_OVERLAP", "0") == "1"
+
+
 def train_step(model, optimizer, prop, text_input_ids, text_attention_mask, alpha, _prepared=False, **fwd_kw):
     """zero_grad -> forward -> backward -> grad all-reduce -> clip(5.) + AdamW.  Returns the 4 losses (device)."""
-    from . import ops
+    from . import ops, xbert
     rng = ops.step_rng(model.arena().device)
     rng.advance(bump_host=not _prepared)    # fresh dropout / sampler randomness for this step (device-side increment)
     optimizer.zero_grad()
-    losses = model(prop, text_input_ids, text_attention_mask, alpha=alpha, **fwd_kw)
-    loss = losses[0] + losses[1] + losses[2] + losses[3]
-    loss.backward()
     W = world_size()
     A = model.arena()
-    if W > 1:
+    ov = None
+    if W > 1 and _overlap_enabled():
+        ov = getattr(model, "_grad_overlap", None)
+        if ov is None or ov.A is not A:
+            ov = GradOverlap(A)
+            model.__dict__["_grad_overlap"] = ov
+        ov.begin()
+    xbert.set_grad_overlap(ov)
+    try:
+        losses = model(prop, text_input_ids, text_attention_mask, alpha=alpha, **fwd_kw)
+        loss = losses[0] + losses[1] + losses[2] + losses[3]
+        loss.backward()
+    finally:
+        xbert.set_grad_overlap(None)
+    if ov is not None:
+        ov.finish()
+    elif W > 1:
         dist.all_reduce(A.G[A.adam_start:], op=dist.ReduceOp.SUM)
     if hasattr(optimizer, "prepare_step"):
         optimizer.step(skip_flag=model.last_aux["nan_flag"], grad_scale=1.0 / W, prepared=_prepared)

@@ -208,6 +208,15 @@ def _bf16(t):
     return t if t is None or t.dtype == torch.bfloat16 else t.to(torch.bfloat16)
 
 
+# Gradient all-reduce overlapped with backward (trainer.GradOverlap): while set, the first pass of a step that runs a layer
+# marks the layer's input, and the marker's backward hands the layer's gradient range to the communication stream.
+_OVERLAP = [None]
+
+
+def set_grad_overlap(ctx):
+    _OVERLAP[0] = ctx
+
+
 class ModelOutput(SimpleNamespace):
     def __getitem__(self, i):
         return (self.last_hidden_state,)[i]
@@ -281,8 +290,11 @@ class BertModel(nn.Module):
             cross_geom = SimpleNamespace(B=B, Tq=T, Tk=Te, kv_len=None if cmask is None else cmask.kv_len, causal=False)
         fl, nl = cfg.fusion_layer, cfg.num_hidden_layers
         lo, hi = {'text': (0, fl), 'fusion': (fl, nl), 'multi_modal': (0, nl)}[mode]
+        ov = _OVERLAP[0]
         for i in range(lo, hi):
             lw = bd.layers[i]
+            if ov is not None and lw.grad_range is not None and torch.is_grad_enabled() and x.requires_grad and ov.claim(lw.grad_range):
+                x = ops.grad_ready(x, ov.callback(lw.grad_range))
             x = ops.attn_block(x, None, lw.attn, self_geom, p_att, p_hid, bd.anchor)
             if lw.cross is not None:
                 if enc is None:

@@ -44,7 +44,7 @@ def main(out_path):
     mpm = (torch.rand(B, 53, generator=g) < 0.5).float().to(dev)
     neg = [((torch.arange(B) + torch.randint(1, B, (B,), generator=g)) % B).tolist() for _ in range(2)]
     pv, ids, mask = pv.to(dev), ids.to(dev), mask.to(dev)
-    res = {"world": world, "nccl": dist.get_backend()}
+    res = {"world": world, "nccl": dist.get_backend(), "overlap": os.environ.get("SPMM_DDP_OVERLAP", "0")}
     stepper = trainer.GraphedTrainStep(model, opt)
 
     # (1) single-rank gradient of this rank's batch (no reduction), state restored afterwards

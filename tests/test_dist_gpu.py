@@ -14,18 +14,21 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_step_reduces_gradients_and_keeps_replicas_bit_identical(tmp_path):
+@pytest.mark.parametrize("overlap", ["0", "1"], ids=["one_allreduce", "overlapped_buckets"])
+def test_two_rank_step_reduces_gradients_and_keeps_replicas_bit_identical(tmp_path, overlap):
+    """overlap=1: SPMM_DDP_OVERLAP - per-layer all-reduces issued from backward markers on a side stream
+    (trainer.GradOverlap), eager and captured; the reduced gradient must still be the mean of the single-rank ones."""
     out = str(tmp_path / "dist2.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(REPO, "tests", "dist_gpu_worker.py"), out]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=REPO)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=REPO, env=dict(os.environ, SPMM_DDP_OVERLAP=overlap))
     print(r.stdout[-3000:])
     print(r.stderr[-3000:])
     assert r.returncode == 0
     res = json.load(open(out))
     keep = os.environ.get("SPMM_DIST_TEST_LOG")                  # e.g. profiles/r2_dist2_parity.json
     if keep:
-        json.dump(res, open(keep, "w"), indent=1)
+        json.dump(res, open(keep.replace(".json", "_overlap%s.json" % overlap), "w"), indent=1)
     assert res["world"] == 2 and res["nccl"] == "nccl"
     assert res["grad_mean_rel"] < 1e-5, res["grad_mean_rel"]     # float-atomic summation order between two backward runs
     assert res["grad_differs_from_local_rel"] > 1e-2              # the check is not vacuous: ranks hold different batches

@@ -254,6 +254,37 @@ def test_cuda_graph_step_matches_eager_step():
     assert out["eager"][2] == out["graph"][2] and out["eager"][3] == out["graph"][3]
 
 
+@pytest.mark.parametrize("case", ["tiny_b6", "full_b8"])
+def test_layer_gradients_are_final_when_their_all_reduce_is_issued(case):
+    """trainer.GradOverlap hands a layer's gradient range to the communication stream from a marker on the layer's input
+    in the first pass that uses it.  Single-rank check of the ordering argument (no NCCL needed): every range is
+    snapshotted when its marker fires and must be unchanged at the end of backward - i.e. no later kernel added to it -
+    and the markers must cover every encoder layer exactly once (18 layers: 12 text / fusion + 6 property)."""
+    from spmm_b200 import trainer, xbert
+    g = load_golden(case)
+    model = build_model(case)
+    A = model.arena()
+    ov = trainer.GradOverlap(A, check=True)
+    ov.begin()
+    xbert.set_grad_overlap(ov)
+    try:
+        losses = model(g["pv"].to(DEV), g["ids"].to(DEV), g["mask"].to(DEV), alpha=0.4, mpm_mask=g["mpm_mask"].to(DEV),
+                       neg_idx=(g["neg_t2i"], g["neg_i2t"]))
+        sum(losses).backward()
+    finally:
+        xbert.set_grad_overlap(None)
+    torch.cuda.synchronize()
+    n = ov.finish()
+    n_layers = len(model.text_encoder.bert.encoder.layer) + len(model.property_encoder.encoder.layer)
+    assert n == n_layers, (n, n_layers)
+    spans = sorted(ov.done)
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))             # disjoint
+    covered = sum(hi - lo for lo, hi in spans)
+    print("ranges reduced early: %d, covering %.1f %% of the gradient arena" % (n, 100.0 * covered / (A.n_total - A.adam_start)))
+    assert covered > 0.9 * (A.n_total - A.adam_start)
+    assert all(float(A.G[lo:hi].abs().sum()) > 0 for lo, hi in spans)      # the snapshots were taken of real gradients
+
+
 def test_fit_driver_runs_the_reference_hooks():
     """trainer.fit = the reference's `pl.Trainer(...).fit` body (SPMM_pretrain.py:12-37) through training_step /
     on_train_epoch_end with pre-tokenised batches: finite losses, queue pointer advanced by B per step, lr warm-up."""
