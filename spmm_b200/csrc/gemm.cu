@@ -898,29 +898,29 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
         }
         if (p.colsum != nullptr && !two_phase) {
           // Column sums of this group's 128 x 64 box from the staged bf16 values (what a separate pass over the stored
-          // tensor would read), while the bulk store drains: thread = (column pair, row quarter), 32 rows each, rows >= M
-          // skipped.  Row 32rq + 8a + b of the box sits at base + a*1024 + b*128 + ((u ^ b) << 4).
-          const int t = threadIdx.x - 128 - 128 * g;
-          const int cp = t & 31, rq = t >> 5;
+          // tensor would read), while the bulk store drains.  Warp q of the group owns column pairs 8q .. 8q+7; lane =
+          // (row part rp, column pair): rows 4i + rp, i = 0..31 (consecutive rows sit in different swizzle units, so the
+          // four row parts hit different banks); two shuffle steps fold the row parts, then ONE atomic per column from
+          // the whole box - same-address atomics from the 48 CTAs of a column tile serialise in L2, so few matter.
+          const int rp = lane >> 3, cp = 8 * q + (lane & 7);
           const int u = cp >> 2;
-          const uint8_t* base = staging + g * STG_BOX_BYTES + (32 * rq) * 128 + (cp & 3) * 4;
-          const int rmax = p.M - (m0 + 32 * rq);               // rows of this quarter that exist (may be <= 0)
+          const uint8_t* base = staging + g * STG_BOX_BYTES + (cp & 3) * 4;
+          const int rmax = p.M - m0;                           // rows of this CTA's tile that exist
           f32x2 acc_a = 0ull, acc_b = 0ull;
 #pragma unroll
-          for (int b = 0; b < 8; ++b) {
-            const uint8_t* pb = base + b * 128 + ((u ^ b) << 4);
-#pragma unroll
-            for (int a = 0; a < 4; a += 2) {
-              const uint32_t w0 = *reinterpret_cast<const uint32_t*>(pb + a * 1024);
-              const uint32_t w1 = *reinterpret_cast<const uint32_t*>(pb + (a + 1) * 1024);
-              if (8 * a + b < rmax) acc_a = add2(acc_a, bf16x2_to_f32x2(w0));
-              if (8 * (a + 1) + b < rmax) acc_b = add2(acc_b, bf16x2_to_f32x2(w1));
-            }
+          for (int i = 0; i < 32; i += 2) {
+            const int r0 = 4 * i + rp, r1 = 4 * (i + 1) + rp;
+            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(base + r0 * 128 + ((u ^ (r0 & 7)) << 4));
+            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(base + r1 * 128 + ((u ^ (r1 & 7)) << 4));
+            if (r0 < rmax) acc_a = add2(acc_a, bf16x2_to_f32x2(w0));
+            if (r1 < rmax) acc_b = add2(acc_b, bf16x2_to_f32x2(w1));
           }
           float s0, s1;
           upk2(add2(acc_a, acc_b), s0, s1);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
           const int col = n0 + 64 * g + 2 * cp;
-          if (col < p.N) {
+          if (rp == 0 && col < p.N) {
             atomicAdd(p.colsum + col, s0);
             atomicAdd(p.colsum + col + 1, s1);
           }
