@@ -151,9 +151,10 @@ int spmm_enqueue(float* prop_queue, float* text_queue, const float* prop_feats, 
 int spmm_lm_loss_fwd_bwd(const void* logits, const void* teacher_logits, int ld, const int64_t* ids, int B, int L,
                          int V, float alpha, const float* alpha_dev, const int* valid_len, float* loss, void* dlogits,
                          float* workspace, void* stream);
-/* ITM (SPMM_models.py:201-206): logits = x[3B,2H] . W^T + b, CE with labels [1]*B + [0]*2B. */
+/* ITM (SPMM_models.py:201-206): logits = x[3B,2H] . W^T + b, CE with labels [1]*B + [0]*2B.
+ * dw / db are accumulated into (+=); workspace: >= 3 * n_rows floats. */
 int spmm_itm_loss_fwd_bwd(const void* x, const float* w, const float* b, int n_rows, int n_pos, int D, float* loss,
-                          void* dx, float* dw, float* db, void* stream);
+                          void* dx, float* dw, float* db, float* workspace, void* stream);
 /* MPM tail (SPMM_models.py:251-254): pred = t . w + b over rows (b, j<n_prop); masked MSE * 5. */
 int spmm_mpm_loss_fwd_bwd(const void* t, const float* w, const float* b, const float* pv, const float* mpm_mask,
                           int batch, int n_prop, int H, float* loss, void* dt, float* dw, float* db, float* workspace,

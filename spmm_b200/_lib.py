@@ -52,7 +52,7 @@ SIGNATURES = {
     "spmm_sample_negatives": (i32, [vp, vp, i32, u64, u64, vp, vp, vp]),
     "spmm_enqueue": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]),
     "spmm_lm_loss_fwd_bwd": (i32, [vp, vp, i32, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
-    "spmm_itm_loss_fwd_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "spmm_itm_loss_fwd_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "spmm_mpm_loss_fwd_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "spmm_decode_embed": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp]),
     "spmm_decode_attn_self": (i32, [vp, i32, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, f32, vp]),
@@ -91,7 +91,8 @@ def lib():
 
 
 # kernels launched per C call (for bench.py's `gpu_launches` claim)
-KERNELS_PER_CALL = {"spmm_itc_fwd_bwd": 6, "spmm_lm_loss_fwd_bwd": 3, "spmm_mpm_loss_fwd_bwd": 3, "spmm_enqueue": 2}
+KERNELS_PER_CALL = {"spmm_itc_fwd_bwd": 6, "spmm_lm_loss_fwd_bwd": 3, "spmm_mpm_loss_fwd_bwd": 3, "spmm_enqueue": 2,
+                    "spmm_itm_loss_fwd_bwd": 2}
 _launches = 0
 
 

@@ -22,6 +22,7 @@ import torch
 from . import kernels as K
 
 ALIGN = 64
+SHARD_ALIGN = 8 * 64      # (n_total - adam_start) is a multiple of this: equal, aligned optimiser shards for 1/2/4/8 ranks
 MODEL_PAIRS = (("property_encoder", "property_encoder_m"), ("property_proj", "property_proj_m"),
                ("text_encoder", "text_encoder_m"), ("text_proj", "text_proj_m"))
 TAIL_MODULES = ("itm_head", "property_embed", "property_mtr_head")
@@ -75,6 +76,8 @@ class ParamArena:
             off += _pad(p.numel())
         if n_ema_entries == len(entries):
             self.n_ema = off
+        first_pad = _pad(entries[0][1].numel()) if entries[0][0] == NEVER_GRAD else 0
+        off += (-(off - first_pad)) % SHARD_ALIGN      # the optimiser range splits evenly over up to 8 ranks (16-byte shards)
         self.n_total = off
         first = entries[0]
         self.adam_start = _pad(first[1].numel()) if first[0] == NEVER_GRAD else 0

@@ -94,52 +94,57 @@ __global__ void lm_final_kernel(const float* ws, int B, int L, float alpha, cons
   *loss = (1.f - alpha) * ws[1] / (float)(B * (Lv - 1)) + alpha * ws[2] / ws[0];
 }
 
-// ------------------------------------------------------------------ ITM head + CE (single CTA; ~1 MFLOP)
-__global__ void __launch_bounds__(1024)
-itm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int n_rows,
-           int n_pos, int D, float* loss, __nv_bfloat16* __restrict__ dx, float* dw, float* db) {
-  extern __shared__ float sdl[];  // [n_rows][2] dlogits
+// ------------------------------------------------------------------ ITM head + CE
+// Two small multi-CTA kernels (a single CTA took 0.22 ms for ~1 MFLOP: 288 dependent row loads per column thread).
+// Phase 1, warp per row: logits, CE, d logits -> workspace, dx row.  Phase 2, thread per column x row split: dw (atomics
+// over the splits), and in CTA (0,0) db and the loss (fixed summation order).
+__global__ void __launch_bounds__(256)
+itm_rows_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int n_rows,
+                int n_pos, int D, float* __restrict__ ws, __nv_bfloat16* __restrict__ dx) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  float a0 = 0.f, a1 = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float xv = bf2f(x[(size_t)r * D + k]);
+    a0 += xv * w[k];
+    a1 += xv * w[D + k];
+  }
+  a0 = warp_sum(a0) + bias[0];
+  a1 = warp_sum(a1) + bias[1];
+  const float mx = fmaxf(a0, a1);
+  const float e0 = __expf(a0 - mx), e1 = __expf(a1 - mx), se = e0 + e1;
+  const int label = r < n_pos ? 1 : 0;
+  const float d0 = (e0 / se - (label == 0 ? 1.f : 0.f)) / n_rows, d1 = (e1 / se - (label == 1 ? 1.f : 0.f)) / n_rows;
+  if (lane == 0) {
+    ws[2 * r] = d0;
+    ws[2 * r + 1] = d1;
+    ws[2 * n_rows + r] = mx + __logf(se) - (label ? a1 : a0);
+  }
+  for (int k = lane; k < D; k += 32) dx[(size_t)r * D + k] = f2bf(d0 * w[k] + d1 * w[D + k]);
+}
+
+__global__ void __launch_bounds__(256)
+itm_cols_kernel(const __nv_bfloat16* __restrict__ x, int n_rows, int D, const float* __restrict__ ws, float* loss, float* dw,
+                float* db) {
   __shared__ float sh[32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  float lsum = 0.f;
-  for (int r = warp; r < n_rows; r += nw) {
-    float a0 = 0.f, a1 = 0.f;
-    for (int k = lane; k < D; k += 32) {
-      const float xv = bf2f(x[(size_t)r * D + k]);
-      a0 += xv * w[k];
-      a1 += xv * w[D + k];
-    }
-    a0 = warp_sum(a0) + bias[0];
-    a1 = warp_sum(a1) + bias[1];
-    const float mx = fmaxf(a0, a1);
-    const float e0 = __expf(a0 - mx), e1 = __expf(a1 - mx), se = e0 + e1;
-    const int label = r < n_pos ? 1 : 0;
-    if (lane == 0) {
-      lsum += mx + __logf(se) - (label ? a1 : a0);
-      sdl[2 * r + 0] = (e0 / se - (label == 0 ? 1.f : 0.f)) / n_rows;
-      sdl[2 * r + 1] = (e1 / se - (label == 1 ? 1.f : 0.f)) / n_rows;
-    }
-  }
-  lsum = block_sum(lsum, sh);  // contains the __syncthreads that publishes sdl
-  if (threadIdx.x == 0) *loss = lsum / n_rows;
-  for (int k = threadIdx.x; k < D; k += blockDim.x) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  const int per = (n_rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(n_rows, r0 + per);
+  if (k < D) {
     float g0 = 0.f, g1 = 0.f;
-    for (int r = 0; r < n_rows; ++r) {
+    for (int r = r0; r < r1; ++r) {
       const float xv = bf2f(x[(size_t)r * D + k]);
-      g0 += sdl[2 * r] * xv;
-      g1 += sdl[2 * r + 1] * xv;
+      g0 += ws[2 * r] * xv;
+      g1 += ws[2 * r + 1] * xv;
     }
-    dw[k] += g0;
-    dw[D + k] += g1;
+    atomicAdd(dw + k, g0);
+    atomicAdd(dw + D + k, g1);
   }
-  if (threadIdx.x < 2) {
-    float g = 0.f;
-    for (int r = 0; r < n_rows; ++r) g += sdl[2 * r + threadIdx.x];
-    db[threadIdx.x] += g;
-  }
-  for (int i = threadIdx.x; i < n_rows * D; i += blockDim.x) {
-    const int r = i / D, k = i % D;
-    dx[i] = f2bf(sdl[2 * r] * w[k] + sdl[2 * r + 1] * w[D + k]);
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    float l = 0.f, b0 = 0.f, b1 = 0.f;
+    for (int r = threadIdx.x; r < n_rows; r += 256) { l += ws[2 * n_rows + r]; b0 += ws[2 * r]; b1 += ws[2 * r + 1]; }
+    l = block_sum(l, sh); b0 = block_sum(b0, sh); b1 = block_sum(b1, sh);
+    if (threadIdx.x == 0) { *loss = l / n_rows; db[0] += b0; db[1] += b1; }
   }
 }
 
@@ -232,10 +237,14 @@ extern "C" int spmm_lm_loss_fwd_bwd(const void* logits, const void* teacher_logi
 }
 
 extern "C" int spmm_itm_loss_fwd_bwd(const void* x, const float* w, const float* b, int n_rows, int n_pos, int D,
-                                     float* loss, void* dx, float* dw, float* db, void* stream) {
-  SPMM_ARG(x && w && b && loss && dx && dw && db && n_rows > 0 && D > 0 && n_rows <= 4096);
-  itm_kernel<<<1, 1024, (size_t)n_rows * 2 * sizeof(float), (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, w, b, n_rows, n_pos, D, loss, (__nv_bfloat16*)dx, dw, db);
+                                     float* loss, void* dx, float* dw, float* db, float* workspace, void* stream) {
+  SPMM_ARG(x && w && b && loss && dx && dw && db && workspace && n_rows > 0 && D > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  itm_rows_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>((const __nv_bfloat16*)x, w, b, n_rows, n_pos, D, workspace,
+                                                    (__nv_bfloat16*)dx);
+  SPMM_CHECK_LAUNCH();
+  const int splits = n_rows >= 64 ? 8 : 1;
+  itm_cols_kernel<<<dim3((D + 255) / 256, splits), 256, 0, st>>>((const __nv_bfloat16*)x, n_rows, D, workspace, loss, dw, db);
   SPMM_CHECK_LAUNCH();
   return 0;
 }

@@ -197,8 +197,9 @@ def itm_loss(x, w, b, n_pos, dw, db):
     n_rows, D = x.shape
     loss = torch.empty((), device=x.device, dtype=torch.float32)
     dx = torch.empty_like(x)
+    ws = torch.empty(3 * n_rows, device=x.device, dtype=torch.float32)
     call("spmm_itm_loss_fwd_bwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), n_rows, n_pos, D, loss.data_ptr(),
-         dx.data_ptr(), dw.data_ptr(), db.data_ptr(), _st())
+         dx.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), _st())
     return loss, dx
 
 

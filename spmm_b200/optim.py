@@ -58,12 +58,57 @@ class FusedClipAdamW(torch.optim.Optimizer):
                 grp["weight_decay"], max(self.t, 1), sumsq=A.sumsq, max_norm=self.max_norm, grad_scale=grad_scale,
                 skip_flag=skip_flag, hyper_dev=self.hyper_dev)
 
+    @torch.no_grad()
+    def step_sharded(self, world, rank, skip_flag=None, prepared=False):
+        """Data-parallel step with the optimiser work split over the ranks (ZeRO-1 style): reduce-scatter of the gradient
+        arena (this rank receives the SUM of its 1/world slice), clip + AdamW on that slice only, all-gather of the
+        updated fp32 weights.  Same bytes on the wire as the all-reduce it replaces (reduce-scatter + all-gather), but
+        the 0.9 ms of sumsq + AdamW shrink by the world size.  Every rank ends with bit-identical weights (the gather
+        distributes one copy); the Adam moments of a slice live on its owner only."""
+        import torch.distributed as dist
+        A, g0 = self.A, self.A.adam_start
+        grp = self.param_groups[0]
+        if not prepared:
+            self.prepare_step()
+        n = A.n_total - g0
+        assert n % world == 0
+        sh = n // world
+        lo = g0 + rank * sh
+        G, P = A.G[g0:], A.P[g0:]
+        gs = A.G[lo:lo + sh]
+        dist.reduce_scatter_tensor(gs, G, op=dist.ReduceOp.SUM)              # in place: output = own slice of the input
+        K.grad_sumsq(gs, A.sumsq)
+        dist.all_reduce(A.sumsq, op=dist.ReduceOp.SUM)                       # global sum g^2 (same bits on every rank)
+        K.adam_tick(self.t_dev, self.lr_dev, self.hyper_dev, grp["betas"][0], grp["betas"][1], skip_flag)
+        a, b = rank * sh, (rank + 1) * sh
+        K.adamw(A.P[lo:lo + sh], gs, self.exp_avg[a:b], self.exp_avg_sq[a:b], grp["lr"], grp["betas"][0], grp["betas"][1],
+                grp["eps"], grp["weight_decay"], max(self.t, 1), sumsq=A.sumsq, max_norm=self.max_norm,
+                grad_scale=1.0 / world, skip_flag=skip_flag, hyper_dev=self.hyper_dev)
+        dist.all_gather_into_tensor(P, A.P[lo:lo + sh])                       # in place: input = own slice of the output
+        self.sharded = (world, rank)
+
     def grad_norm(self, grad_scale=1.0):
         """Total gradient L2 norm of the last step() (device scalar)."""
         return self.A.sumsq.sqrt() * grad_scale
 
+    def _full_moments(self):
+        """With a sharded step each rank owns the moments of its slice: gather them for a checkpoint."""
+        sharded = getattr(self, "sharded", None)
+        if sharded is None:
+            return self.exp_avg, self.exp_avg_sq
+        import torch.distributed as dist
+        world, rank = sharded
+        sh = self.exp_avg.numel() // world
+        out = []
+        for t in (self.exp_avg, self.exp_avg_sq):
+            full = torch.empty_like(t)
+            dist.all_gather_into_tensor(full, t[rank * sh:(rank + 1) * sh].contiguous())
+            out.append(full)
+        return out
+
     def state_dict(self):
-        return {"t": int(self.t_dev), "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+        m1, m2 = self._full_moments()
+        return {"t": int(self.t_dev), "exp_avg": m1, "exp_avg_sq": m2,
                 "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
 
     def load_state_dict(self, sd):

@@ -73,6 +73,12 @@ def _overlap_enabled():
     return os.environ.get("SPMM_DDP_OVERLAP", "0") == "1"
 
 
+def _sharded_enabled():
+    """SPMM_DP_SHARDED=1: reduce-scatter + per-rank AdamW slice + all-gather instead of all-reduce + replicated AdamW."""
+    import os
+    return os.environ.get("SPMM_DP_SHARDED", "0") == "1"
+
+
 def train_step(model, optimizer, prop, text_input_ids, text_attention_mask, alpha, _prepared=False, **fwd_kw):
     """zero_grad -> forward -> backward -> grad all-reduce -> clip(5.) + AdamW.  Returns the 4 losses (device)."""
     from . import ops, xbert
@@ -82,7 +88,8 @@ def train_step(model, optimizer, prop, text_input_ids, text_attention_mask, alph
     W = world_size()
     A = model.arena()
     ov = None
-    if W > 1 and _overlap_enabled():
+    sharded = W > 1 and _sharded_enabled() and hasattr(optimizer, "step_sharded") and dist.get_backend() == "nccl"
+    if W > 1 and _overlap_enabled() and not sharded:
         ov = getattr(model, "_grad_overlap", None)
         if ov is None or ov.A is not A:
             ov = GradOverlap(A)
@@ -95,6 +102,9 @@ def train_step(model, optimizer, prop, text_input_ids, text_attention_mask, alph
         loss.backward()
     finally:
         xbert.set_grad_overlap(None)
+    if sharded:
+        optimizer.step_sharded(W, dist.get_rank(), skip_flag=model.last_aux["nan_flag"], prepared=_prepared)
+        return losses
     if ov is not None:
         ov.finish()
     elif W > 1:
@@ -120,6 +130,10 @@ class GraphedTrainStep:
     multiple of `len_bucket` so that a few graphs cover all widths; the pad columns are masked keys / dead rows, and
     the LM loss ignores them through `valid_len`, so the losses equal those of the [B, L] batch.  Graphs share one
     memory pool (they never run concurrently) and are evicted least-recently-used beyond `max_graphs`.
+
+    Note for callers that also run eager steps on the same model: drop the loss tensors of those steps before the first
+    capture - a live autograd graph keeps its AccumulateGrad nodes (for `temp`) bound to the stream they were created
+    on, and re-using them inside a capture is a CUDA error (cudaErrorStreamCaptureImplicit).
     """
 
     def __init__(self, model, optimizer, max_graphs=16, warmup_steps=2, len_bucket=8):

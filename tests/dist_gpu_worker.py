@@ -44,7 +44,8 @@ def main(out_path):
     mpm = (torch.rand(B, 53, generator=g) < 0.5).float().to(dev)
     neg = [((torch.arange(B) + torch.randint(1, B, (B,), generator=g)) % B).tolist() for _ in range(2)]
     pv, ids, mask = pv.to(dev), ids.to(dev), mask.to(dev)
-    res = {"world": world, "nccl": dist.get_backend(), "overlap": os.environ.get("SPMM_DDP_OVERLAP", "0")}
+    res = {"world": world, "nccl": dist.get_backend(), "overlap": os.environ.get("SPMM_DDP_OVERLAP", "0"),
+           "sharded": os.environ.get("SPMM_DP_SHARDED", "0")}
     stepper = trainer.GraphedTrainStep(model, opt)
 
     # (1) single-rank gradient of this rank's batch (no reduction), state restored afterwards
@@ -54,7 +55,10 @@ def main(out_path):
     sum(losses).backward()
     g_local = A.G[A.adam_start:].clone()
     stepper._restore(snap)
-    del snap
+    # no autograd graph of an eager step may outlive this point: its AccumulateGrad nodes (for `temp`, the anchor) carry
+    # the legacy stream they were created on and would be re-used by the capture below ("legacy stream depends on a
+    # capturing stream")
+    del snap, losses
     # the real step: all-reduce(SUM) inside, 1/W folded into clip + AdamW
     p_before = A.P.clone()
     trainer.train_step(model, opt, pv, ids, mask, 0.4, mpm_mask=mpm, neg_idx=neg)
@@ -62,8 +66,16 @@ def main(out_path):
     parts = [torch.empty_like(g_local) for _ in range(world)]
     dist.all_gather(parts, g_local)
     mean = torch.stack(parts).sum(0) / world
-    res["grad_mean_rel"] = float((g_sum / world - mean).norm() / mean.norm())
-    res["grad_differs_from_local_rel"] = float((g_sum / world - g_local).norm() / mean.norm())   # ranks see different data
+    if os.environ.get("SPMM_DP_SHARDED", "0") == "1":       # reduce-scatter: the SUM lives in this rank's slice only
+        sh = g_sum.numel() // world
+        sl = slice(rank * sh, (rank + 1) * sh)
+    else:
+        sl = slice(0, g_sum.numel())
+    res["grad_mean_rel"] = float((g_sum[sl] / world - mean[sl]).norm() / mean[sl].norm())
+    res["grad_differs_from_local_rel"] = float((g_sum[sl] / world - g_local[sl]).norm() / mean[sl].norm())   # ranks see different data
+    worst = torch.tensor([res["grad_mean_rel"]], device=dev)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)            # every rank's slice must pass
+    res["grad_mean_rel"] = float(worst)
     res["weights_moved"] = bool(not torch.equal(p_before, A.P))
     # (3) queue rows [r*B, (r+1)*B) = rank r's momentum features of step 1
     f = model.last_aux["feat_prop_m"]
