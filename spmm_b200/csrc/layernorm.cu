@@ -26,8 +26,10 @@ __device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
+// 6 CTAs per SM (40 registers): the 768 CTAs of a 6144-row call fit in ONE wave of 888 slots; at 5 per SM the last 28
+// CTAs formed a second wave and the latency-bound kernel took two row latencies instead of one.
 template <int NCH>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, 6)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
               float eps, unsigned long long seed, uint32_t thresh16, float inv_keep, const unsigned long long* salt) {
@@ -164,12 +166,12 @@ ln_bwd_param_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
 #pragma unroll
   for (int j = 0; j < 8; ++j) ag[j] = ab[j] = as[j] = 0.f;
   if (c0 < H) {
-    for (int r = r0 + w; r < r1; r += 8) {
+    // two rows per iteration, all six 16-byte loads issued before the first use: the loop is bound by load latency
+    // (a warp walks ~8 rows), so memory-level parallelism is what shortens it
+    auto accumulate = [&](int r, const uint4& pd, const uint4& pxv, const uint4& pb, float mu, float rs) {
       float d[8], xv[8];
-      load8(dy + (size_t)r * H + c0, d);
-      load8(x + (size_t)r * H + c0, xv);
-      const float mu = mean[r], rs = rstd[r];
-#pragma unroll
+      unpack_bf16x2(pd.x, d[0], d[1]); unpack_bf16x2(pd.y, d[2], d[3]); unpack_bf16x2(pd.z, d[4], d[5]); unpack_bf16x2(pd.w, d[6], d[7]);
+      unpack_bf16x2(pxv.x, xv[0], xv[1]); unpack_bf16x2(pxv.y, xv[2], xv[3]); unpack_bf16x2(pxv.z, xv[4], xv[5]); unpack_bf16x2(pxv.w, xv[6], xv[7]);
       if (out_thresh) {
 #pragma unroll
         for (int j = 0; j < 8; j += 2) drop_pair(out_key, (uint32_t)r * H + c0 + j, out_thresh, out_inv_keep, d[j], d[j + 1]);
@@ -181,10 +183,25 @@ ln_bwd_param_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
       }
       if (dbias != nullptr) {
         float bv[8];
-        load8(branch + (size_t)r * H + c0, bv);
+        unpack_bf16x2(pb.x, bv[0], bv[1]); unpack_bf16x2(pb.y, bv[2], bv[3]); unpack_bf16x2(pb.z, bv[4], bv[5]); unpack_bf16x2(pb.w, bv[6], bv[7]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) as[j] += bv[j];
       }
+    };
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    for (int r = r0 + w; r < r1; r += 16) {
+      const int rb = r + 8;
+      const bool two = rb < r1;
+      const uint4 d0 = *reinterpret_cast<const uint4*>(dy + (size_t)r * H + c0);
+      const uint4 x0 = *reinterpret_cast<const uint4*>(x + (size_t)r * H + c0);
+      const uint4 b0 = dbias != nullptr ? *reinterpret_cast<const uint4*>(branch + (size_t)r * H + c0) : z4;
+      const uint4 d1 = two ? *reinterpret_cast<const uint4*>(dy + (size_t)rb * H + c0) : z4;
+      const uint4 x1 = two ? *reinterpret_cast<const uint4*>(x + (size_t)rb * H + c0) : z4;
+      const uint4 b1 = (two && dbias != nullptr) ? *reinterpret_cast<const uint4*>(branch + (size_t)rb * H + c0) : z4;
+      const float mu0 = mean[r], rs0 = rstd[r];
+      const float mu1 = two ? mean[rb] : 0.f, rs1 = two ? rstd[rb] : 0.f;
+      accumulate(r, d0, x0, b0, mu0, rs0);
+      if (two) accumulate(rb, d1, x1, b1, mu1, rs1);
     }
   }
 #pragma unroll
