@@ -44,21 +44,28 @@ def world_any(flag):
     return flag
 
 
-def gather_world_feats(feats):
+def gather_world_feats(feats, flag=None):
     """concat_all_gather (reference SPMM_models.py:389-399) for a stacked [2, B, E] feature tensor: ONE collective for
-    both modalities; result [2, W*B, E] with rank r's rows at [r*B, (r+1)*B) exactly like torch.cat(tensors_gather)."""
+    both modalities; result [2, W*B, E] with rank r's rows at [r*B, (r+1)*B) exactly like torch.cat(tensors_gather).
+    `flag` (0-d device float, optional) rides in the same collective: returns (feats, max of the ranks' flags) - the NaN
+    guard is one decision for the whole world without a second synchronisation point in the step."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return feats
+        return feats if flag is None else (feats, flag)
     W_ = dist.get_world_size()
     feats = feats.contiguous()
+    n = feats.numel()
+    send = feats.reshape(-1) if flag is None else torch.cat([feats.reshape(-1), flag.reshape(1).to(feats.dtype)])
     if dist.get_backend() == "nccl":
-        gathered = torch.empty((W_,) + tuple(feats.shape), device=feats.device, dtype=feats.dtype)
-        dist.all_gather_into_tensor(gathered, feats)
+        gathered = torch.empty((W_, send.numel()), device=feats.device, dtype=feats.dtype)
+        dist.all_gather_into_tensor(gathered, send)
     else:
-        parts = [torch.empty_like(feats) for _ in range(W_)]
-        dist.all_gather(parts, feats)
+        parts = [torch.empty_like(send) for _ in range(W_)]
+        dist.all_gather(parts, send)
         gathered = torch.stack(parts)
-    return gathered.permute(1, 0, 2, 3).reshape(2, -1, feats.shape[-1]).contiguous()
+    out = gathered[:, :n].reshape((W_,) + tuple(feats.shape)).permute(1, 0, 2, 3).reshape(2, -1, feats.shape[-1]).contiguous()
+    if flag is None:
+        return out
+    return out, gathered[:, n].max().reshape(flag.shape)
 
 
 class AttrDict(dict):
@@ -270,9 +277,7 @@ class SPMM(*((_Base,) if _Base is not nn.Module else (_StandaloneHooks, nn.Modul
             alpha = float(alpha)
         loss_ita = ops.itc(z_prop, z_text, self.temp, z_prop_m, z_text_m, self.prop_queue_km, self.text_queue_km,
                            alpha, side)                                                                 # :102-131
-        # NaN guard (:132-133): one decision for the whole data-parallel world (enqueue, optimiser step and the returned
-        # losses all key off this flag), taken before anything global is touched
-        nan_flag = world_any(side["nan_flag"])
+        nan_flag = side["nan_flag"]        # rank-local here; made world-wide together with the feature gather below
 
         # ================ ITM (:135-206) ================ #
         def fusion(q, q_mask, kv, kv_mask, dec=False):
@@ -296,7 +301,9 @@ class SPMM(*((_Base,) if _Base is not nn.Module else (_StandaloneHooks, nn.Modul
         vl = torch.cat([out_prop, out_text], dim=-1)              # rows [0,B) positives, [B,3B) negatives (:199-201)
         loss_itm = ops.itm_loss(vl, W["itm"], B)
 
-        self._dequeue_and_enqueue(side["feat_prop_m"], side["feat_text_m"], nan_flag)                   # :208
+        # NaN guard (:132-133): ONE decision for the whole data-parallel world - the gathered queue rows and the reduced
+        # gradients are global, so a rank skipping alone would diverge for good.  The flag travels with the features.
+        nan_flag = self._dequeue_and_enqueue(side["feat_prop_m"], side["feat_text_m"], nan_flag)         # :208
 
         # ================ MLM (:210-238) ================ #
         V = te.config.vocab_size
@@ -333,10 +340,15 @@ class SPMM(*((_Base,) if _Base is not nn.Module else (_StandaloneHooks, nn.Modul
     @torch.no_grad()
     def _dequeue_and_enqueue(self, prop_feat, text_feat, skip_flag=None):
         """SPMM_models.py:271-286.  Rank-local feats are all-gathered (one NCCL call for both modalities)."""
-        feats = gather_world_feats(torch.stack([prop_feat, text_feat]))     # [2, W*B, E] fp32, rank-major like torch.cat
+        stacked = torch.stack([prop_feat, text_feat])                       # [2, W*B, E] fp32, rank-major like torch.cat
+        if skip_flag is None:
+            feats = gather_world_feats(stacked)
+        else:
+            feats, skip_flag = gather_world_feats(stacked, skip_flag)       # flag -> max over the world
         n = feats.shape[1]
         assert self.queue_size % n == 0                                      # :279
         K.enqueue(self.prop_queue_km, self.text_queue_km, feats[0], feats[1], self.queue_ptr, skip_flag)
+        return skip_flag
 
     # ------------------------------------------------------------------ Lightning-shaped hooks (reference :345-386)
     # With pytorch_lightning installed the class IS a LightningModule and `optimizers()`, `lr_schedulers()`, `log`,

@@ -157,6 +157,8 @@ def _dist_worker(rank, world, path, out):
     # the NaN guard is one decision for the whole world: a flag raised on rank 1 only must be seen by rank 0
     from spmm_b200.SPMM_models import world_any
     flag = world_any(torch.tensor(1.0 if rank == 1 else 0.0))
+    g2, flag2 = gather_world_feats(feats, torch.tensor(1.0 if rank == 1 else 0.0))   # flag riding on the feature gather
+    assert torch.equal(g2, g) and float(flag2) == 1.0
     if rank == 0:
         torch.save({"g": g, "grad": grad / world, "flag": flag}, out)
     dist.barrier()
