@@ -395,7 +395,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 constexpr int BN2 = 256;
 constexpr int B2_STAGE_BYTES = (BN2 / 2) * BK * 2;               // this CTA's half of the B tile
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;     // 32 KB
-constexpr int kStages2 = 5;   // default ring depth; the two-output variant runs 3 stages + a second staging tile
+constexpr int kStages2 = 5;
 constexpr int STG_BOX_BYTES = 128 * 128;                         // [128 rows][128 B], 16-byte units XOR (row & 7)
 constexpr int STG_BYTES = 4 * STG_BOX_BYTES;                     // 64 KB: 128 x 256 bf16, or 128 x 128 f32
 constexpr int kThreads2 = 128 + 16 * 32;   // TMA / MMA / TMEM-alloc / side-loader warps + 16 epilogue warps
@@ -427,7 +427,6 @@ __device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* 
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -601,24 +600,19 @@ __device__ __forceinline__ void epi2_generic(const GemmParams& p, float (&v)[EC]
   }
 }
 
-// kStages x 32 KB operand ring + kStg x 64 KB epilogue staging = 224 KB either way: <5, 1> for every problem but the
-// two-output (GELU + gelu') one, whose 64-column sub-phases alternate between two staging tiles so that the bulk stores of
-// one sub-phase drain while the next one computes (<3, 2>; the epilogue, not the mainloop, bounds that kernel).
-template <int kStages, int kStg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
-  static_assert(kStages * STAGE2_BYTES + kStg * STG_BYTES == kStages2 * STAGE2_BYTES + STG_BYTES, "same shared-memory footprint");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* staging0 = smem + kStages * STAGE2_BYTES;                        // 1024-aligned
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging0 + kStg * STG_BYTES);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tfull_bar = empty_bar + kStages;
+  uint8_t* staging = smem + kStages2 * STAGE2_BYTES;                       // 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STG_BYTES);
+  uint64_t* empty_bar = full_bar + kStages2;
+  uint64_t* tfull_bar = empty_bar + kStages2;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* side_full = tempty_bar + 2;     // side operand of the current tile landed in the staging tile
   uint64_t* stage_free = side_full + 1;     // both halves' stores of the previous tile have read the staging tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
-  float* s_bias = reinterpret_cast<float*>(staging0 + kStg * STG_BYTES + 512);
+  float* s_bias = reinterpret_cast<float*>(staging + STG_BYTES + 512);
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -642,7 +636,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
     if (has_pre) tma_prefetch_desc(&maps.pre);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kStages2; ++s) {
       mbar_init(&full_bar[s], 1);    // leader's copy is the one in use: 1 arrive (leader producer) + tx of both CTAs
       mbar_init(&empty_bar[s], 1);   // multicast commit from the leader's MMA thread
     }
@@ -692,7 +686,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
 #pragma unroll
           for (int c = 0; c < BN2 / 128; ++c) tma_load_2d_2sm(sb + c * 8192, &maps.b, &full_bar[stage], nb0 + c * 64, kb * BK);
         }
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == kStages2) { stage = 0; phase ^= 1; }
         if (tile == pair && kb == kb0) trace_mark(p, 2);
       }
     }
@@ -717,7 +711,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
         if (p.debug_nomma) {
           mbar_arrive_rank(&empty_bar[stage], 0);
           mbar_arrive_rank(&empty_bar[stage], 1);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
           continue;
         }
         const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
@@ -731,7 +725,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
           tc_mma_bf16_2sm(d_tmem, adesc, bdesc, idesc, ((kb - kb0) | k) != 0);
         }
         tc_commit_2sm(&empty_bar[stage]);   // both CTAs' producers may refill this slot
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == kStages2) { stage = 0; phase ^= 1; }
       }
       if (p.debug_nomma) { mbar_arrive_rank(&tfull_bar[acc], 0); mbar_arrive_rank(&tfull_bar[acc], 1); }
       else tc_commit_2sm(&tfull_bar[acc]);  // both CTAs' epilogues
@@ -752,7 +746,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       mbar_expect_tx(side_full, nbox * STG_BOX_BYTES);
 #pragma unroll
       for (int b = 0; b < 4; ++b)
-        if (n0 + 64 * b < p.N) tma_load_2d(staging0 + b * STG_BOX_BYTES, &maps.side, side_full, n0 + 64 * b, m0);
+        if (n0 + 64 * b < p.N) tma_load_2d(staging + b * STG_BOX_BYTES, &maps.side, side_full, n0 + 64 * b, m0);
       ph ^= 1;
     }
   } else if (warp >= 4) {
@@ -789,7 +783,6 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
     const bool side_tma = has_side && p.side_tma;
     const bool side_reg = has_side && !p.side_tma;
     const int nsub = two_phase ? 2 : 1, nch = two_phase ? 2 : 4;
-    uint32_t ring = 0;                 // sub-phase counter: selects the staging tile when there are two
     int acc = 0;
     uint32_t acc_phase = 0, side_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -809,7 +802,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       };
       load_side(n0 + chunk_col(0, 0), side_next);   // in flight while the MMAs of this tile are still running
       // staging free (previous stores have read it), previous bias reads and column sums done
-      if (st_elected) { if (kStg == 2) bulk_wait_read1(); else bulk_wait_read0(); }
+      if (st_elected) bulk_wait_read0();
       bar_sync_named(allbar, 32 * 16);
       if (p.bias != nullptr) {
         const int t = threadIdx.x - 128;
@@ -825,9 +818,8 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       uint32_t rr[EC];
       if (n0 + chunk_col(0, 0) < p.N) tmem_ld16(taddr + chunk_col(0, 0), rr);
       for (int sub = 0; sub < nsub; ++sub) {
-        uint8_t* staging = staging0 + (kStg == 2 ? (ring & 1) * STG_BYTES : 0);
         if (sub > 0) {
-          if (st_elected) { if (kStg == 2) bulk_wait_read1(); else bulk_wait_read0(); }
+          if (st_elected) bulk_wait_read0();
           if (half_sync) bar_sync_named(hbar, 256); else bar_sync_named(gbar, 128);
           if (warp == 4 && lane == 0 && tile == pair) trace_mark(p, 14);
         }
@@ -904,7 +896,6 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
           }
           bulk_commit();
         }
-        ++ring;
         if (p.colsum != nullptr && !two_phase) {
           // Column sums of this group's 128 x 64 box from the staged bf16 values (what a separate pass over the stored
           // tensor would read), while the bulk store drains.  Warp q of the group owns column pairs 8q .. 8q+7; lane =
@@ -1021,23 +1012,17 @@ static int g_use_2cta = 1;
 static int g_side_reg = 0;    // debug A/B: 1 = side operand by register prefetch even where TMA staging is possible
 static int g_no_colsum = 0;   // debug A/B: 1 = fused column sums computed by the separate kernel instead
 
-static int g_single_staging = 0;   // debug A/B: 1 = the two-output problems also run the <5, 1> instantiation
-
 static int launch2(const Gemm2Maps& maps, const GemmParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel<kStages2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(gemm2_bf16_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN2 - 1) / BN2) * p.splits;
   int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
   if (g_max_ctas > 0 && 2 * pairs > g_max_ctas) pairs = g_max_ctas / 2 > 0 ? g_max_ctas / 2 : 1;
-  const bool two_out = p.pre != nullptr && !(p.flags & SPMM_GEMM_OUT_F32) && !g_single_staging;
-  cudaError_t le = two_out ? launch_pdl(gemm2_bf16_kernel<3, 2>, dim3(2 * pairs), dim3(kThreads2), SMEM2_BYTES, st, maps, p)
-                           : launch_pdl(gemm2_bf16_kernel<kStages2, 1>, dim3(2 * pairs), dim3(kThreads2), SMEM2_BYTES, st, maps, p);
+  cudaError_t le = launch_pdl(gemm2_bf16_kernel, dim3(2 * pairs), dim3(kThreads2), SMEM2_BYTES, st, maps, p);
   if (le != cudaSuccess) return (int)le;
   return 0;
 }
@@ -1066,7 +1051,6 @@ extern "C" int spmm_gemm_debug_config(int mn_lbo_bytes, int mn_sbo_bytes, int fo
   g_use_2cta = (force_bn & 0x40000) ? 0 : 1;  // bit 18 disables the 2-CTA kernel
   g_side_reg = (force_bn & 0x100000) ? 1 : 0;
   g_no_colsum = (force_bn & 0x200000) ? 1 : 0;
-  g_single_staging = (force_bn & 0x400000) ? 1 : 0;
   g_nomma = (force_bn & 0x20000) ? 1 : ((force_bn & 0x80000) ? 2 : 0);   // bit 19: MMA-only (no TMA, garbage results)     // bit 17: skip MMAs (TMA-only pipeline timing; results are garbage)
   g_max_ctas = max_ctas;
   return 0;
