@@ -224,7 +224,8 @@ class GraphedTrainStep:
     def __call__(self, prop, ids, mask, alpha, mpm_mask=None):
         """One training step on the batch; returns the 4 losses (static device tensor, overwritten by the next call)."""
         from . import ops
-        key = (prop.shape[0], self.bucket_len(ids.shape[1]), mpm_mask is not None)
+        # dropout on / off is baked into the captured kernels: train and eval mode get their own graphs
+        key = (prop.shape[0], self.bucket_len(ids.shape[1]), mpm_mask is not None, bool(getattr(self.model, "training", True)))
         st = self.graphs.get(key)
         if st is None:
             st = self._capture(key, prop, ids, mask, alpha, mpm_mask)

@@ -281,7 +281,7 @@ def test_graph_stepper_buckets_lengths_and_keeps_lru_order():
         return g.graphs[key]
     g._capture = fake_capture
     g._fill = lambda st, *a: filled.append(a[3])
-    g.model = SimpleNamespace(arena=lambda: SimpleNamespace(device="cpu"))
+    g.model = SimpleNamespace(arena=lambda: SimpleNamespace(device="cpu"), training=True)
     g.opt = SimpleNamespace(prepare_step=lambda: None)
     g.losses = torch.zeros(4)
     import spmm_b200.ops as ops
@@ -295,6 +295,6 @@ def test_graph_stepper_buckets_lengths_and_keeps_lru_order():
         ops.step_rng = orig
     # 60/64/57/62 share the 64-bucket; 70 -> 72; 99 -> 104 evicts the least recently used (72: the 64-bucket was just
     # replayed for L=62); the second L=70 batch captures 72 again and evicts 64
-    assert captured == [(6, 64, False), (6, 72, False), (6, 104, False), (6, 72, False)]
-    assert list(g.graphs) == [(6, 104, False), (6, 72, False)]
+    assert captured == [(6, 64, False, True), (6, 72, False, True), (6, 104, False, True), (6, 72, False, True)]
+    assert list(g.graphs) == [(6, 104, False, True), (6, 72, False, True)]
     assert filled == [0.1, 0.2, 0.4]                   # replays refresh the device scalars; alpha never keys a graph
