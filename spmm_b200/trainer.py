@@ -74,9 +74,10 @@ def _overlap_enabled():
 
 
 def _sharded_enabled():
-    """SPMM_DP_SHARDED=1: reduce-scatter + per-rank AdamW slice + all-gather instead of all-reduce + replicated AdamW."""
+    """Reduce-scatter + per-rank AdamW slice + all-gather instead of all-reduce + replicated AdamW: the default under
+    NCCL (measured at N = 8: 42.73 vs 43.05 ms per step); SPMM_DP_SHARDED=0 selects the single all-reduce."""
     import os
-    return os.environ.get("SPMM_DP_SHARDED", "0") == "1"
+    return os.environ.get("SPMM_DP_SHARDED", "1") == "1"
 
 
 def train_step(model, optimizer, prop, text_input_ids, text_attention_mask, alpha, _prepared=False, **fwd_kw):
@@ -88,7 +89,8 @@ def train_step(model, optimizer, prop, text_input_ids, text_attention_mask, alph
     W = world_size()
     A = model.arena()
     ov = None
-    sharded = W > 1 and _sharded_enabled() and hasattr(optimizer, "step_sharded") and dist.get_backend() == "nccl"
+    sharded = (W > 1 and _sharded_enabled() and hasattr(optimizer, "step_sharded") and dist.get_backend() == "nccl"
+               and (A.n_total - A.adam_start) % W == 0)
     if W > 1 and _overlap_enabled() and not sharded:
         ov = getattr(model, "_grad_overlap", None)
         if ov is None or ov.A is not A:

@@ -45,7 +45,7 @@ def main(out_path):
     neg = [((torch.arange(B) + torch.randint(1, B, (B,), generator=g)) % B).tolist() for _ in range(2)]
     pv, ids, mask = pv.to(dev), ids.to(dev), mask.to(dev)
     res = {"world": world, "nccl": dist.get_backend(), "overlap": os.environ.get("SPMM_DDP_OVERLAP", "0"),
-           "sharded": os.environ.get("SPMM_DP_SHARDED", "0")}
+           "sharded": os.environ.get("SPMM_DP_SHARDED", "1")}
     stepper = trainer.GraphedTrainStep(model, opt)
 
     # (1) single-rank gradient of this rank's batch (no reduction), state restored afterwards
@@ -66,7 +66,7 @@ def main(out_path):
     parts = [torch.empty_like(g_local) for _ in range(world)]
     dist.all_gather(parts, g_local)
     mean = torch.stack(parts).sum(0) / world
-    if os.environ.get("SPMM_DP_SHARDED", "0") == "1":       # reduce-scatter: the SUM lives in this rank's slice only
+    if os.environ.get("SPMM_DP_SHARDED", "1") == "1":       # reduce-scatter: the SUM lives in this rank's slice only
         sh = g_sum.numel() // world
         sl = slice(rank * sh, (rank + 1) * sh)
     else:
