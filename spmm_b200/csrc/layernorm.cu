@@ -89,11 +89,8 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma; optionally dx_branch = dx * dropout mask.
-// Two passes over the row: the first accumulates the two row sums, the second RE-READS dy / x (L1 / L2 hits: a warp's
-// row is 3 KB) and writes the outputs.  Holding 48 fp32 values per lane between the passes cost 77 registers = 3 CTAs
-// per SM = 1.5-1.7 waves for a 5184 / 6144-row call; re-reading needs ~40 and the call fits in one wave (6 CTAs per SM).
 template <int NCH>
-__global__ void __launch_bounds__(LN_WARPS * 32, 6)
+__global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                  __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_branch, int rows, int H,
@@ -107,31 +104,28 @@ ln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float mu = mean[row], rs = rstd[row];
-  // g = dy (o dropout) * gamma and xhat of one 8-column chunk
-  auto chunk = [&](int col, float (&xh)[8], float (&g)[8]) {
-    float d[8], gm[8];
-    load8(x + (size_t)row * H + col, xh);
-    load8(dy + (size_t)row * H + col, d);
-    load8f(gamma + col, gm);
-    if (out_thresh) {  // forward applied dropout after the affine: dy_affine = dy * mask / keep
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) drop_pair(out_key, (uint32_t)row * H + col + j, out_thresh, out_inv_keep, d[j], d[j + 1]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      xh[j] = (xh[j] - mu) * rs;
-      g[j] = d[j] * gm[j];
-    }
-  };
+  float xh[NCH][8], g[NCH][8];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int col = (lane + 32 * c) * 8;
     if (col < H) {
-      float xh[8], g[8];
-      chunk(col, xh, g);
+      float d[8], gm[8];
+      load8(x + (size_t)row * H + col, xh[c]);
+      load8(dy + (size_t)row * H + col, d);
+      load8f(gamma + col, gm);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s1 += g[j]; s2 += g[j] * xh[j]; }
+      if (out_thresh) {  // forward applied dropout after the affine: dy_affine = dy * mask / keep
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) drop_pair(out_key, (uint32_t)row * H + col + j, out_thresh, out_inv_keep, d[j], d[j + 1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[c][j] = (xh[c][j] - mu) * rs;
+        g[c][j] = d[j] * gm[j];
+        s1 += g[c][j];
+        s2 += g[c][j] * xh[c][j];
+      }
     }
   }
   s1 = warp_sum(s1) / H;
@@ -140,10 +134,9 @@ ln_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
   for (int c = 0; c < NCH; ++c) {
     const int col = (lane + 32 * c) * 8;
     if (col < H) {
-      float xh[8], g[8], o[8];
-      chunk(col, xh, g);
+      float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = rs * (g[j] - s1 - xh[j] * s2);
+      for (int j = 0; j < 8; ++j) o[j] = rs * (g[c][j] - s1 - xh[c][j] * s2);
       store8(dx + (size_t)row * H + col, o);
       if (dx_branch) {
 #pragma unroll
