@@ -61,7 +61,9 @@ int spmm_gemm_debug_trace_ring(void* buf, long slots);   /* one 148 x 16 x u64 s
 /* ------------------------------------------------------------------ attention core (xbert.py:305-354)
  * softmax(Q K^T * scale + mask) V per (batch, head), head_dim 64, Tq,Tk <= 128.  q/k/v/o rows are
  * tokens (b*T + t) with leading dims ld*, head h at column 64*h.  kv_len[b] = number of valid keys
- * (pad mask, xbert.py:947 / invert_attention_mask), NULL = all; causal = is_decoder mask (xbert.py:911-931).
+ * (pad mask, xbert.py:947 / invert_attention_mask), NULL = all; causal = is_decoder mask (xbert.py:911-931):
+ * 0 = none, 1 = every batch element, 1 + n = batch elements with index >= n only (lets a bidirectional and a causal
+ * pass over the same weights share one launch: rows [0, n) bidirectional, rows [n, batch) causal).
  * kv_batch_stride_rows = Tk normally, 0 broadcasts one K/V over the batch (beam decode,
  * d_pv2smiles_single.py:29-36).  lse[B*heads*Tq] fp32 is saved for backward. */
 int spmm_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,

@@ -263,14 +263,27 @@ class SPMM(*((_Base,) if _Base is not nn.Module else (_StandaloneHooks, nn.Modul
         te, te_m = self.text_encoder, self.text_encoder_m
 
         properties = ops.pv_tokens(pv, mpm_mask, W["pv"], self._anchor)                                # :82-88
-        prop_embeds = self.property_encoder(inputs_embeds=properties).last_hidden_state                 # :90
+        # Passes that run the SAME weights on the SAME input are batched into one 2B-row pass (rows are independent; the
+        # per-row causal flag lives in the attention kernels): the bidirectional property pass (:90) with the causal one
+        # of MPM (:242), and the bidirectional text pass (:94) with the first six - text-only - layers of the causal
+        # MLM pass (:224), likewise for the momentum text encoder.  Every GEMM / LayerNorm launch of those layers then
+        # carries twice the rows (two waves instead of two single-wave launches) and the weights are read once.
+        fl = te.config.fusion_layer
+        L = ids.shape[1]
+        props2 = torch.cat([properties, properties], dim=0)
+        pe2 = self.property_encoder(inputs_embeds=props2, causal_from=B).last_hidden_state
+        prop_embeds, pc = torch.split(pe2, B, dim=0)                                                    # :90, :242
         z_prop = ops.proj_f32(prop_embeds[:, 0, :], W["property_proj"])                                 # :92
-        text_embeds = te.bert(ids, attention_mask=tmask, mode='text').last_hidden_state                 # :94
+        ids2 = torch.cat([ids, ids], dim=0)
+        tmask2 = MaskInfo(kv_len=torch.cat([tmask.kv_len, tmask.kv_len]))
+        te2 = te.bert(ids2, attention_mask=tmask2, mode='text', causal_from=B).last_hidden_state
+        text_embeds, mlm_lower = torch.split(te2, B, dim=0)                                             # :94, :224 (layers < fl)
         z_text = ops.proj_f32(text_embeds[:, 0, :], W["text_proj"])                                     # :95
         with torch.no_grad():                                                                           # :98-106
             prop_embeds_m = self.property_encoder_m(inputs_embeds=properties).last_hidden_state
             z_prop_m = ops.proj_f32(prop_embeds_m[:, 0, :], W["property_proj_m"])
-            text_embeds_m = te_m.bert(ids, attention_mask=tmask, mode='text').last_hidden_state
+            te2_m = te_m.bert(ids2, attention_mask=tmask2, mode='text', causal_from=B).last_hidden_state
+            text_embeds_m, mlm_lower_m = te2_m[:B], te2_m[B:]                                           # :104, :215
             z_text_m = ops.proj_f32(text_embeds_m[:, 0, :], W["text_proj_m"])
         side = {}
         if not torch.is_tensor(alpha):
@@ -307,15 +320,17 @@ class SPMM(*((_Base,) if _Base is not nn.Module else (_StandaloneHooks, nn.Modul
 
         # ================ MLM (:210-238) ================ #
         V = te.config.vocab_size
+        # the text-only layers of both causal passes already ran above (batched with the bidirectional text passes)
         with torch.no_grad():
-            h_m = te_m.bert(ids, attention_mask=tmask, encoder_hidden_states=prop_embeds_m, is_decoder=True).last_hidden_state
-            logits_m = ops.lm_logits(h_m.view(-1, H), te_m.bert._bundles().head, V, te.logit_ld())
-        h = te.bert(ids, attention_mask=tmask, encoder_hidden_states=prop_embeds, is_decoder=True).last_hidden_state
-        loss_mlm = ops.lm_head_loss(h.view(-1, H), logits_m, ids, te.bert._bundles().head, alpha, V, valid_len)
+            h_m = te_m.bert(encoder_embeds=mlm_lower_m, attention_mask=tmask, encoder_hidden_states=prop_embeds_m,
+                            is_decoder=True, mode='fusion').last_hidden_state
+            logits_m = ops.lm_logits(h_m.reshape(-1, H), te_m.bert._bundles().head, V, te.logit_ld())
+        h = te.bert(encoder_embeds=mlm_lower, attention_mask=tmask, encoder_hidden_states=prop_embeds, is_decoder=True,
+                    mode='fusion').last_hidden_state
+        loss_mlm = ops.lm_head_loss(h.reshape(-1, H), logits_m, ids, te.bert._bundles().head, alpha, V, valid_len)
 
         # ================ MPM (:240-254) ================ #
-        pc = self.property_encoder(inputs_embeds=properties, is_decoder=True).last_hidden_state
-        po = fusion(pc, None, text_embeds, tmask, dec=True)
+        po = fusion(pc, None, text_embeds, tmask, dec=True)          # pc: the causal half of the batched property pass
         loss_mpm = ops.mtr_head_loss(po.view(-1, H), pv, mpm_mask, W["mtr"])      # already x5 (:256)
 
         self.last_aux = {"neg_t2i": neg_t2i, "neg_i2t": neg_i2t, "nan_flag": nan_flag, "mpm_mask": mpm_mask,

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_tc_kernel(const __grid
       const int h = a.pair ? t.h0 + slot : t.h0;
       const bool valid = (h < a.heads) && (i < a.Tq);
       const int klen = a.kv_len ? min(__ldg(a.kv_len + t.b), a.Tk) : a.Tk;
-      const int jmax = a.causal ? min(klen, i + 1) : klen;     // keys [0, jmax) are visible to this row
+      const int jmax = (a.causal > 0 && t.b >= a.causal - 1) ? min(klen, i + 1) : klen;   // keys [0, jmax) are visible to this row
       const int bh = t.b * a.heads + h;
       const uint32_t ph = nl & 1;
       if (tr) at_mark(a, 4 + 6 * nl);
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
       const bool head_ok = h < a.heads;
       const bool valid = head_ok && (i < a.Tq);
       const int klen = a.kv_len ? min(__ldg(a.kv_len + b), a.Tk) : a.Tk;
-      const int jmax = a.causal ? min(klen, i + 1) : klen;
+      const int jmax = (a.causal > 0 && b >= a.causal - 1) ? min(klen, i + 1) : klen;
       const int bh = b * a.heads + h;
       const float lse2 = valid ? __ldg(a.lse + (size_t)bh * a.Tq + i) * AT_LOG2E : 0.f;
       const uint32_t ph = n & 1;

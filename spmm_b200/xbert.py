@@ -247,7 +247,9 @@ class BertModel(nn.Module):
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
                 inputs_embeds=None, encoder_embeds=None, encoder_hidden_states=None, encoder_attention_mask=None,
                 past_key_values=None, use_cache=None, output_attentions=None, output_hidden_states=None,
-                return_dict=True, is_decoder=False, mode='multi_modal'):
+                return_dict=True, is_decoder=False, mode='multi_modal', causal_from=None):
+        """`causal_from` (SPMM.forward only): the batch holds two passes over the same weights - rows [0, causal_from)
+        attend bidirectionally, rows [causal_from, B) causally - so both share every GEMM / LayerNorm launch."""
         if past_key_values is not None or output_attentions or output_hidden_states or head_mask is not None:
             raise NotImplementedError("unused on the SPMM hot path")
         cfg = self.config
@@ -276,7 +278,7 @@ class BertModel(nn.Module):
             raise ValueError("You have to specify either input_ids or inputs_embeds or encoder_embeds")
         smask = MaskInfo.of(attention_mask)
         self_geom = SimpleNamespace(B=B, Tq=T, Tk=T, kv_len=None if smask is None else smask.kv_len,
-                                    causal=bool(is_decoder))
+                                    causal=(1 + int(causal_from)) if causal_from is not None else int(bool(is_decoder)))
         enc = None
         cross_geom = None
         if encoder_hidden_states is not None:

@@ -339,6 +339,33 @@ def test_attention_fwd_bwd(B, h, Tq, Tk, causal, ragged):
     assert rel_err(dv, flat(vf.grad, Tk)) < 2e-2, ("dv", rel_err(dv, flat(vf.grad, Tk)))
 
 
+@pytest.mark.parametrize("B,first_causal,T", [(6, 3, 54), (192, 96, 54), (5, 0, 64), (4, 4, 99)])
+def test_attention_causal_from_a_batch_index(B, first_causal, T):
+    """`causal = 1 + n` masks only the problems with batch index >= n: the step batches the bidirectional and the
+    causal pass of one encoder (same weights, SPMM_models.py:95-103 and :172-180 of the reference) into one launch."""
+    h, H = 12, 768
+    qkv = rnd(B * T, 3 * H, dtype=BF, seed=11)
+    q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+    kv_len = torch.randint(T // 3, T + 1, (B,), generator=torch.Generator().manual_seed(5)).to(DEV).int()
+    o = torch.empty(B * T, H, device=DEV, dtype=BF)
+    lse = torch.empty(B * h * T, device=DEV)
+    K.attn_fwd(q, k, v, o, lse, B, h, T, T, kv_len, 1 + first_causal, 0.125)
+    do = rnd(B * T, H, dtype=BF, seed=12)
+    dqkv = torch.zeros(B * T, 3 * H, device=DEV, dtype=BF)
+    K.attn_bwd(do, q, k, v, o, lse, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], B, h, T, T, kv_len,
+               1 + first_causal, 0.125)
+    # the same rows through two launches with a uniform flag are the answer, bit for bit
+    o2, lse2, dqkv2 = torch.empty_like(o), torch.empty_like(lse), torch.zeros_like(dqkv)
+    for lo, hi, flag in ((0, first_causal, 0), (first_causal, B, 1)):
+        if hi == lo:
+            continue
+        r = slice(lo * T, hi * T)
+        K.attn_fwd(q[r], k[r], v[r], o2[r], lse2[lo * h * T:hi * h * T], hi - lo, h, T, T, kv_len[lo:hi].contiguous(), flag, 0.125)
+        K.attn_bwd(do[r], q[r], k[r], v[r], o2[r], lse2[lo * h * T:hi * h * T], dqkv2[r, :H], dqkv2[r, H:2 * H], dqkv2[r, 2 * H:],
+                   hi - lo, h, T, T, kv_len[lo:hi].contiguous(), flag, 0.125)
+    assert torch.equal(o, o2) and torch.equal(lse, lse2) and torch.equal(dqkv, dqkv2)
+
+
 @pytest.mark.parametrize("B,h,Tq,Tk,causal", [(3, 12, 64, 64, False), (2, 4, 54, 99, False), (2, 12, 99, 99, True)])
 def test_attention_dropout_forward_backward_share_the_mask(B, h, Tq, Tk, causal):
     """With attention dropout the forward and backward kernels regenerate the same keep mask from (seed, head, i, j).
