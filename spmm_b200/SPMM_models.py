@@ -293,9 +293,6 @@ class SPMM(*((_Base,) if _Base is not nn.Module else (_StandaloneHooks, nn.Modul
         nan_flag = side["nan_flag"]        # rank-local here; made world-wide together with the feature gather below
 
         # ================ ITM (:135-206) ================ #
-        def fusion(q, q_mask, kv, kv_mask, dec=False):
-            return te.bert(encoder_embeds=q, attention_mask=q_mask, encoder_hidden_states=kv,
-                           encoder_attention_mask=kv_mask, is_decoder=dec, mode='fusion').last_hidden_state
         if neg_idx is None:
             # per-step variation comes from the device RNG salt (ops.StepRng), so the draw is CUDA-graph safe
             neg_t2i, neg_i2t = ops.sample_negatives(side, self.sampler_seed, 0)                         # :154-178
@@ -304,13 +301,22 @@ class SPMM(*((_Base,) if _Base is not nn.Module else (_StandaloneHooks, nn.Modul
             neg_i2t = torch.as_tensor(neg_idx[1], device=pv.device, dtype=torch.int32)
         prop_neg = ops.gather_rows(prop_embeds, neg_t2i)
         text_neg = ops.gather_rows(text_embeds, neg_i2t)
-        # The reference runs the positive pairs (B) and the negative pairs (2B) as four fusion passes (:137-198).  The
-        # rows are independent, so they are batched into two passes of 3B pairs: [pos | neg-prop | neg-text].
-        tmask3 = MaskInfo(kv_len=torch.cat([tmask.kv_len, tmask.kv_len, tmask.kv_len[neg_i2t.long()]]))
-        text3 = torch.cat([text_embeds, text_embeds, text_neg], dim=0)
-        prop3 = torch.cat([prop_embeds, prop_neg, prop_embeds], dim=0)
-        out_prop = fusion(prop3, None, text3, tmask3)[:, 0, :]
-        out_text = fusion(text3, tmask3, prop3, None)[:, 0, :]
+        # The reference runs the positive pairs (B) and the negative pairs (2B) as four fusion passes (:137-198), then
+        # the fusion layers of the causal MLM pass (:224, text queries over property keys) and the causal MPM pass (:245,
+        # property queries over text keys) - all through the SAME six fusion layers.  Rows are independent, so they are
+        # batched into two passes of 4B rows: [pos | neg-prop | neg-text | causal], the last B rows with the causal flag.
+        kv = tmask.kv_len
+        tmask4 = MaskInfo(kv_len=torch.cat([kv, kv, kv[neg_i2t.long()], kv]))
+        prop_q = torch.cat([prop_embeds, prop_neg, prop_embeds, pc], dim=0)
+        text_kv = torch.cat([text_embeds, text_embeds, text_neg, text_embeds], dim=0)
+        fo_prop = te.bert(encoder_embeds=prop_q, attention_mask=None, encoder_hidden_states=text_kv,
+                          encoder_attention_mask=tmask4, mode='fusion', causal_from=3 * B).last_hidden_state
+        out_prop, po = fo_prop[:3 * B, 0, :], fo_prop[3 * B:]                                           # :137-198, :245
+        text_q = torch.cat([text_embeds, text_embeds, text_neg, mlm_lower], dim=0)
+        prop_kv = torch.cat([prop_embeds, prop_neg, prop_embeds, prop_embeds], dim=0)
+        fo_text = te.bert(encoder_embeds=text_q, attention_mask=tmask4, encoder_hidden_states=prop_kv,
+                          mode='fusion', causal_from=3 * B).last_hidden_state
+        out_text, h = fo_text[:3 * B, 0, :], fo_text[3 * B:]                                            # :137-198, :224
         vl = torch.cat([out_prop, out_text], dim=-1)              # rows [0,B) positives, [B,3B) negatives (:199-201)
         loss_itm = ops.itm_loss(vl, W["itm"], B)
 
@@ -320,17 +326,16 @@ class SPMM(*((_Base,) if _Base is not nn.Module else (_StandaloneHooks, nn.Modul
 
         # ================ MLM (:210-238) ================ #
         V = te.config.vocab_size
-        # the text-only layers of both causal passes already ran above (batched with the bidirectional text passes)
+        # the online causal pass already ran above (text-only layers with the text pass, fusion layers with ITM); the
+        # momentum one has its text-only layers done
         with torch.no_grad():
             h_m = te_m.bert(encoder_embeds=mlm_lower_m, attention_mask=tmask, encoder_hidden_states=prop_embeds_m,
                             is_decoder=True, mode='fusion').last_hidden_state
             logits_m = ops.lm_logits(h_m.reshape(-1, H), te_m.bert._bundles().head, V, te.logit_ld())
-        h = te.bert(encoder_embeds=mlm_lower, attention_mask=tmask, encoder_hidden_states=prop_embeds, is_decoder=True,
-                    mode='fusion').last_hidden_state
         loss_mlm = ops.lm_head_loss(h.reshape(-1, H), logits_m, ids, te.bert._bundles().head, alpha, V, valid_len)
 
         # ================ MPM (:240-254) ================ #
-        po = fusion(pc, None, text_embeds, tmask, dec=True)          # pc: the causal half of the batched property pass
+        # po: the causal quarter of the batched property-query fusion pass above
         loss_mpm = ops.mtr_head_loss(po.view(-1, H), pv, mpm_mask, W["mtr"])      # already x5 (:256)
 
         self.last_aux = {"neg_t2i": neg_t2i, "neg_i2t": neg_i2t, "nan_flag": nan_flag, "mpm_mask": mpm_mask,
