@@ -65,16 +65,22 @@ int spmm_gemm_debug_trace_ring(void* buf, long slots);   /* one 148 x 16 x u64 s
  * 0 = none, 1 = every batch element, 1 + n = batch elements with index >= n only (lets a bidirectional and a causal
  * pass over the same weights share one launch: rows [0, n) bidirectional, rows [n, batch) causal).
  * kv_batch_stride_rows = Tk normally, 0 broadcasts one K/V over the batch (beam decode,
- * d_pv2smiles_single.py:29-36).  lse[B*heads*Tq] fp32 is saved for backward. */
+ * d_pv2smiles_single.py:29-36).  lse[B*heads*Tq] fp32 is saved for backward.
+ * kv_index (optional, int32[batch] on the device) with kv_batches > 0: batch element b attends to the K/V rows of
+ * batch element kv_index[b] of a [kv_batches * Tk]-row K/V buffer (kv_len stays per b).  The ITM pass of
+ * SPMM_models.py:137-198 pairs the SAME encoder states with several query batches (positives, hard negatives), so
+ * their key/value projection is computed once per distinct state instead of once per pair.  In spmm_attn_bwd dk/dv
+ * stay per batch element b ([batch * Tk] rows); spmm_segment_sum_rows_bf16 folds them onto the distinct states. */
 int spmm_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                   float* lse, int batch, int heads, int Tq, int Tk, const int* kv_len, int causal,
-                  int kv_batch_stride_rows, float scale, float dropout_p, unsigned long long seed, void* stream);
+                  int kv_batch_stride_rows, float scale, float dropout_p, unsigned long long seed,
+                  const int* kv_index, int kv_batches, void* stream);
 int spmm_attn_debug_trace(void* buf);   /* debug: 32 x u64 %globaltimer stamps per CTA of the next forward launches */
 int spmm_attn_bwd(const void* d_o, int lddo, const void* q, int ldq, const void* k, int ldk, const void* v,
                   int ldv, const void* o, int ldo, const float* lse, void* dq, int lddq, void* dk, int lddk,
                   void* dv, int lddv, int batch, int heads, int Tq, int Tk, const int* kv_len, int causal,
                   float scale, float dropout_p, unsigned long long seed, float* dbias_q, float* dbias_k, float* dbias_v,
-                  void* stream);
+                  const int* kv_index, int kv_batches, void* stream);
 /* dbias_q/k/v (optional, all or none; [heads*64] fp32 each): += column sums of dq / dk / dv, i.e. the bias gradients of
  * the query / key / value projections (autograd of xbert.py:280-298), taken from the tiles the kernel already holds. */
 
@@ -114,6 +120,10 @@ int spmm_add_bf16(void* dst, const void* src, int64_t n, void* stream); /* dst +
 int spmm_dgelu_bf16(const void* d_act, const void* pre_act, void* d_pre, int64_t n, void* stream); /* d_pre = d_act * gelu'(pre) */
 int spmm_gather_rows_bf16(const void* src, const int* idx, void* dst, int n_idx, int64_t row_elems, void* stream);
 int spmm_scatter_add_rows_bf16(void* dst, const int* idx, const void* src, int n_idx, int64_t row_elems, void* stream);
+/* dst[t] = sum of src[r] over r with idx[r] == t, t < n_dst (fp32 accumulation in ascending r, written once; rows no r
+ * maps to become zero); n_idx <= 1024.  Autograd of the gathers / shared K/V of SPMM_models.py:165-198. */
+int spmm_segment_sum_rows_bf16(void* dst, int n_dst, const int* idx, const void* src, int n_idx, int64_t row_elems,
+                               void* stream);
 
 /* ------------------------------------------------------------------ ITC / SPC head (SPMM_models.py:92-131)
  * feats are raw projection outputs z[B,E] (fp32); the kernel L2-normalises (F.normalize, :92,95,101,105),

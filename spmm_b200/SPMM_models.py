@@ -308,14 +308,17 @@ class SPMM(*((_Base,) if _Base is not nn.Module else (_StandaloneHooks, nn.Modul
         kv = tmask.kv_len
         tmask4 = MaskInfo(kv_len=torch.cat([kv, kv, kv[neg_i2t.long()], kv]))
         prop_q = torch.cat([prop_embeds, prop_neg, prop_embeds, pc], dim=0)
-        text_kv = torch.cat([text_embeds, text_embeds, text_neg, text_embeds], dim=0)
-        fo_prop = te.bert(encoder_embeds=prop_q, attention_mask=None, encoder_hidden_states=text_kv,
-                          encoder_attention_mask=tmask4, mode='fusion', causal_from=3 * B).last_hidden_state
+        # keys/values: every pair reads one of the B distinct encoder states, so their projection runs on B states
+        # (not 4B pairs) and the attention kernels follow an index
+        own = torch.arange(B, device=pv.device, dtype=torch.int32)
+        fo_prop = te.bert(encoder_embeds=prop_q, attention_mask=None, encoder_hidden_states=text_embeds,
+                          encoder_index=torch.cat([own, own, neg_i2t, own]), encoder_attention_mask=tmask4,
+                          mode='fusion', causal_from=3 * B).last_hidden_state
         out_prop, po = fo_prop[:3 * B, 0, :], fo_prop[3 * B:]                                           # :137-198, :245
         text_q = torch.cat([text_embeds, text_embeds, text_neg, mlm_lower], dim=0)
-        prop_kv = torch.cat([prop_embeds, prop_neg, prop_embeds, prop_embeds], dim=0)
-        fo_text = te.bert(encoder_embeds=text_q, attention_mask=tmask4, encoder_hidden_states=prop_kv,
-                          mode='fusion', causal_from=3 * B).last_hidden_state
+        fo_text = te.bert(encoder_embeds=text_q, attention_mask=tmask4, encoder_hidden_states=prop_embeds,
+                          encoder_index=torch.cat([own, neg_t2i, own, own]), mode='fusion',
+                          causal_from=3 * B).last_hidden_state
         out_text, h = fo_text[:3 * B, 0, :], fo_text[3 * B:]                                            # :137-198, :224
         vl = torch.cat([out_prop, out_text], dim=-1)              # rows [0,B) positives, [B,3B) negatives (:199-201)
         loss_itm = ops.itm_loss(vl, W["itm"], B)

@@ -28,9 +28,10 @@ SIGNATURES = {
     "spmm_gemm_debug_trace": (i32, [vp]),
     "spmm_gemm_debug_trace_ring": (i32, [vp, C.c_long]),
     "spmm_attn_debug_trace": (i32, [vp]),
-    "spmm_attn_fwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, f32, f32, u64, vp]),
+    "spmm_attn_fwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, f32, f32, u64, vp, i32,
+                            vp]),
     "spmm_attn_bwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32,
-                            i32, vp, i32, f32, f32, u64, vp, vp, vp, vp]),
+                            i32, vp, i32, f32, f32, u64, vp, vp, vp, vp, i32, vp]),
     "spmm_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, f32, f32, u64, vp]),
     "spmm_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, u64, f32, u64, vp, vp]),
     "spmm_embed_text_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
@@ -45,6 +46,7 @@ SIGNATURES = {
     "spmm_dgelu_bf16": (i32, [vp, vp, vp, i64, vp]),
     "spmm_gather_rows_bf16": (i32, [vp, vp, vp, i32, i64, vp]),
     "spmm_scatter_add_rows_bf16": (i32, [vp, vp, vp, i32, i64, vp]),
+    "spmm_segment_sum_rows_bf16": (i32, [vp, i32, vp, vp, i32, i64, vp]),
     "spmm_itc_fwd_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, f32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                i64, vp]),
     "spmm_itc_debug_trace": (i32, [vp]),

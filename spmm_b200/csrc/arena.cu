@@ -197,6 +197,64 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(uint4* __restrict
   }
 }
 
+// dst[t] = sum over r with idx[r] == t of src[r] (fp32 accumulation, fixed order, written once; zero when no r maps to
+// t).  gridDim.x = destination rows, gridDim.y = column slices of a row.
+constexpr int kSegMax = 1024;
+__global__ void __launch_bounds__(256) segment_sum_rows_kernel(uint4* __restrict__ dst, const int* __restrict__ idx,
+                                                               const uint4* __restrict__ src, int n_idx,
+                                                               int64_t row_vec) {
+  __shared__ int members[kSegMax];
+  __shared__ int n_members;
+  const int target = blockIdx.x;
+  if (threadIdx.x == 0) n_members = 0;
+  __syncthreads();
+  for (int r = threadIdx.x; r < n_idx; r += blockDim.x)
+    if (idx[r] == target) members[atomicAdd(&n_members, 1)] = r;
+  __syncthreads();
+  const int m = n_members;
+  // ascending source order, whatever order the atomics landed in: the sum is reproducible
+  if (threadIdx.x == 0)
+    for (int i = 1; i < m; ++i) {
+      const int v = members[i];
+      int j = i - 1;
+      for (; j >= 0 && members[j] > v; --j) members[j + 1] = members[j];
+      members[j + 1] = v;
+    }
+  __syncthreads();
+  const int64_t per = (row_vec + gridDim.y - 1) / gridDim.y;
+  const int64_t i0 = blockIdx.y * per, i1 = i0 + per < row_vec ? i0 + per : row_vec;
+  uint4* d = dst + (int64_t)target * row_vec;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int j = 0;
+    for (; j + 4 <= m; j += 4) {          // four rows in flight
+      uint4 b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) b[u] = __ldg(src + (int64_t)members[j + u] * row_vec + i);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float x, y;
+        unpack_bf16x2(b[u].x, x, y); acc[0] += x; acc[1] += y;
+        unpack_bf16x2(b[u].y, x, y); acc[2] += x; acc[3] += y;
+        unpack_bf16x2(b[u].z, x, y); acc[4] += x; acc[5] += y;
+        unpack_bf16x2(b[u].w, x, y); acc[6] += x; acc[7] += y;
+      }
+    }
+    for (; j < m; ++j) {
+      const uint4 b = __ldg(src + (int64_t)members[j] * row_vec + i);
+      float x, y;
+      unpack_bf16x2(b.x, x, y); acc[0] += x; acc[1] += y;
+      unpack_bf16x2(b.y, x, y); acc[2] += x; acc[3] += y;
+      unpack_bf16x2(b.z, x, y); acc[4] += x; acc[5] += y;
+      unpack_bf16x2(b.w, x, y); acc[6] += x; acc[7] += y;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    d[i] = o;
+  }
+}
+
 static inline int flat_grid(int64_t n_items, int per_sm) {
   int64_t blocks = (n_items + 255) / 256;
   const int64_t cap = (int64_t)kNumSMs * per_sm;
@@ -314,6 +372,20 @@ extern "C" int spmm_gather_rows_bf16(const void* src, const int* idx, void* dst,
                                      void* stream) {
   SPMM_ARG(src && idx && dst && n_idx > 0 && row_elems % 8 == 0 && (((uintptr_t)dst | (uintptr_t)src) & 15) == 0);
   gather_rows_kernel<<<n_idx, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, idx, (uint4*)dst, row_elems / 8);
+  SPMM_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spmm_segment_sum_rows_bf16(void* dst, int n_dst, const int* idx, const void* src, int n_idx,
+                                          int64_t row_elems, void* stream) {
+  SPMM_ARG(src && idx && dst && n_dst > 0 && n_idx > 0 && n_idx <= kSegMax && row_elems % 8 == 0 &&
+           (((uintptr_t)dst | (uintptr_t)src) & 15) == 0);
+  const int64_t row_vec = row_elems / 8;
+  int splits = (int)((row_vec + 1023) / 1024);        // <= 4 vectors per thread and slice
+  if (splits < 1) splits = 1;
+  if (splits > 64) splits = 64;
+  segment_sum_rows_kernel<<<dim3(n_dst, splits), 256, 0, (cudaStream_t)stream>>>((uint4*)dst, idx, (const uint4*)src,
+                                                                                  n_idx, row_vec);
   SPMM_CHECK_LAUNCH();
   return 0;
 }

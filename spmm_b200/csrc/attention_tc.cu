@@ -40,6 +40,7 @@ struct AttnFwdArgs {
   float* lse;
   int batch, heads, Tq, Tk;
   const int* kv_len;
+  const int* kv_index;   // optional: batch element b reads the K/V of batch element kv_index[b]
   int causal, kv_bstride;
   float scale;
   unsigned long long seed;
@@ -66,12 +67,12 @@ __device__ __forceinline__ AttnTile attn_decode(const AttnFwdArgs& a, int tile) 
     t.h0 = 2 * (tile % a.hp);
     t.h1 = min(t.h0 + 1, a.heads - 1);
     t.qrow0 = t.qrow1 = t.b * a.Tq;
-    t.krow0 = t.krow1 = t.b * a.kv_bstride;
+    t.krow0 = t.krow1 = (a.kv_index ? __ldg(a.kv_index + t.b) : t.b) * a.kv_bstride;
   } else {
     t.b = tile / a.heads;
     t.h0 = t.h1 = tile % a.heads;
     t.qrow0 = t.b * a.Tq; t.qrow1 = t.qrow0 + 64;
-    t.krow0 = t.b * a.kv_bstride; t.krow1 = t.krow0 + 64;
+    t.krow0 = (a.kv_index ? __ldg(a.kv_index + t.b) : t.b) * a.kv_bstride; t.krow1 = t.krow0 + 64;
   }
   return t;
 }
@@ -401,9 +402,11 @@ int attn_make_map3d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t T, 
 
 int attn_fwd_tc_launch(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, float* lse,
                        int batch, int heads, int Tq, int Tk, const int* kv_len, int causal, int kv_bstride, float scale,
-                       uint32_t thresh16, float inv_keep, unsigned long long seed, cudaStream_t st) {
+                       uint32_t thresh16, float inv_keep, unsigned long long seed, const int* kv_index, int kv_batches,
+                       cudaStream_t st) {
   AttnMaps maps;
-  const uint64_t krows = kv_bstride ? (uint64_t)(batch - 1) * kv_bstride + Tk : (uint64_t)Tk;
+  const int nkv = kv_index ? kv_batches : batch;
+  const uint64_t krows = kv_bstride ? (uint64_t)(nkv - 1) * kv_bstride + Tk : (uint64_t)Tk;
   int rc = attn_make_map(&maps.q, q, (uint64_t)heads * 64, (uint64_t)batch * Tq, ldq);
   if (rc) return rc;
   rc = attn_make_map(&maps.k, k, (uint64_t)heads * 64, krows, ldk);
@@ -415,6 +418,7 @@ int attn_fwd_tc_launch(const void* q, int ldq, const void* k, int ldk, const voi
   AttnFwdArgs a{};
   a.o = reinterpret_cast<__nv_bfloat16*>(o); a.ldo = ldo; a.lse = lse;
   a.batch = batch; a.heads = heads; a.Tq = Tq; a.Tk = Tk; a.kv_len = kv_len; a.causal = causal; a.kv_bstride = kv_bstride;
+  a.kv_index = kv_index;
   a.scale = scale; a.seed = seed; a.thresh16 = thresh16; a.inv_keep = inv_keep; a.salt = spmm_g_rng_salt;
   a.pair = (Tq <= 64 && Tk <= 64) ? 1 : 0;
   a.trace = g_attn_trace;
@@ -460,6 +464,7 @@ struct AttnBwdArgs {
   const float* lse;
   int batch, heads, Tq, Tk;
   const int* kv_len;
+  const int* kv_index;   // optional: K/V of batch element b are rows of batch element kv_index[b]; dK/dV stay per b
   int causal;
   float scale;
   unsigned long long seed;
@@ -511,10 +516,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
   auto decode = [&](int tile, int& b, int& h0, int& h1, int& qrow0, int& qrow1, int& krow0, int& krow1) {
     if (a.pair) {
       b = tile / a.hp; h0 = 2 * (tile % a.hp); h1 = min(h0 + 1, a.heads - 1);
-      qrow0 = qrow1 = b * a.Tq; krow0 = krow1 = b * a.Tk;
+      qrow0 = qrow1 = b * a.Tq; krow0 = krow1 = (a.kv_index ? __ldg(a.kv_index + b) : b) * a.Tk;
     } else {
       b = tile / a.heads; h0 = h1 = tile % a.heads;
-      qrow0 = b * a.Tq; qrow1 = qrow0 + 64; krow0 = b * a.Tk; krow1 = krow0 + 64;
+      qrow0 = b * a.Tq; qrow1 = qrow0 + 64; krow0 = (a.kv_index ? __ldg(a.kv_index + b) : b) * a.Tk; krow1 = krow0 + 64;
     }
   };
 
@@ -768,15 +773,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
 int attn_bwd_tc_launch(const void* d_o, int lddo, const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
                        const float* lse, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int batch, int heads,
                        int Tq, int Tk, const int* kv_len, int causal, float scale, uint32_t thresh16, float inv_keep,
-                       unsigned long long seed, float* dbq, float* dbk, float* dbv, cudaStream_t st) {
+                       unsigned long long seed, float* dbq, float* dbk, float* dbv, const int* kv_index, int kv_batches,
+                       cudaStream_t st) {
   AttnBwdMaps maps;
+  const int nkv = kv_index ? kv_batches : batch;
   int rc = attn_make_map(&maps.q, q, (uint64_t)heads * 64, (uint64_t)batch * Tq, ldq);
   if (rc) return rc;
   rc = attn_make_map(&maps.dout, d_o, (uint64_t)heads * 64, (uint64_t)batch * Tq, lddo);
   if (rc) return rc;
-  rc = attn_make_map(&maps.k, k, (uint64_t)heads * 64, (uint64_t)batch * Tk, ldk);
+  rc = attn_make_map(&maps.k, k, (uint64_t)heads * 64, (uint64_t)nkv * Tk, ldk);
   if (rc) return rc;
-  rc = attn_make_map(&maps.v, v, (uint64_t)heads * 64, (uint64_t)batch * Tk, ldv);
+  rc = attn_make_map(&maps.v, v, (uint64_t)heads * 64, (uint64_t)nkv * Tk, ldv);
   if (rc) return rc;
   rc = attn_make_map3d(&maps.dq, dq, (uint64_t)heads * 64, Tq, batch, lddq);
   if (rc) return rc;
@@ -790,7 +797,7 @@ int attn_bwd_tc_launch(const void* d_o, int lddo, const void* q, int ldq, const 
   a.pair = (Tq <= 64 && Tk <= 64) ? 1 : 0;
   a.hp = (heads + 1) / 2;
   a.num_tiles = a.pair ? batch * a.hp : batch * heads;
-  a.dbq = dbq; a.dbk = dbk; a.dbv = dbv;
+  a.dbq = dbq; a.dbk = dbk; a.dbv = dbv; a.kv_index = kv_index;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);

@@ -48,21 +48,24 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, out=None, out_f32=False, accu
     return out
 
 
-def attn_fwd(q, k, v, out, lse, batch, heads, Tq, Tk, kv_len, causal, scale, dropout_p=0.0, seed=0, kv_bstride=None):
+def attn_fwd(q, k, v, out, lse, batch, heads, Tq, Tk, kv_len, causal, scale, dropout_p=0.0, seed=0, kv_bstride=None,
+             kv_index=None, kv_batches=0):
+    """`kv_index` (int32 [batch]) + `kv_batches`: batch element b reads K/V of element kv_index[b] of a kv_batches-long buffer."""
     call("spmm_attn_fwd", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
          out.data_ptr(), out.stride(0), _p(lse), batch, heads, Tq, Tk, _p(kv_len), int(causal),
-         Tk if kv_bstride is None else kv_bstride, float(scale), float(dropout_p), int(seed), _st())
+         Tk if kv_bstride is None else kv_bstride, float(scale), float(dropout_p), int(seed), _p(kv_index), int(kv_batches),
+         _st())
     return out
 
 
 def attn_bwd(do, q, k, v, o, lse, dq, dk, dv, batch, heads, Tq, Tk, kv_len, causal, scale, dropout_p=0.0, seed=0,
-             dbias=None):
+             dbias=None, kv_index=None, kv_batches=0):
     """`dbias` = (dbq, dbk, dbv) fp32 [heads*64] views: += column sums of dq / dk / dv (projection bias gradients)."""
     dbq, dbk, dbv = dbias if dbias is not None else (None, None, None)
     call("spmm_attn_bwd", do.data_ptr(), do.stride(0), q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
          v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0), lse.data_ptr(), dq.data_ptr(), dq.stride(0),
          dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0), batch, heads, Tq, Tk, _p(kv_len), int(causal),
-         float(scale), float(dropout_p), int(seed), _p(dbq), _p(dbk), _p(dbv), _st())
+         float(scale), float(dropout_p), int(seed), _p(dbq), _p(dbk), _p(dbv), _p(kv_index), int(kv_batches), _st())
 
 
 def layernorm_fwd(x, gamma, beta, eps, save_stats=True, dropout_p=0.0, seed=0):
@@ -133,6 +136,13 @@ def gather_rows(src, idx, n_idx):
 
 def scatter_add_rows(dst, idx, src):
     call("spmm_scatter_add_rows_bf16", dst.data_ptr(), idx.data_ptr(), src.data_ptr(), src.shape[0], src[0].numel(), _st())
+
+
+def segment_sum_rows(src, idx, n_dst):
+    """out[t] = sum of src[r] over idx[r] == t; src [n_idx, ...] bf16, idx int32 on the device."""
+    out = torch.empty((n_dst,) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
+    call("spmm_segment_sum_rows_bf16", out.data_ptr(), n_dst, idx.data_ptr(), src.data_ptr(), src.shape[0], src[0].numel(), _st())
+    return out
 
 
 def _scalar_or_dev(alpha):

@@ -123,7 +123,13 @@ class _AttnBlock(torch.autograd.Function):
         o = torch.empty(M, H, device=x.device, dtype=BF16)
         lse = torch.empty(g.B * W.heads * g.Tq, device=x.device, dtype=torch.float32) if need else None
         seed_a = next_seed() if p_attn > 0 else 0
-        K.attn_fwd(q, k, v, o, lse, g.B, W.heads, g.Tq, g.Tk, g.kv_len, g.causal, scale, p_attn, seed_a)
+        # cross attention over SHARED encoder states: `enc` holds the distinct states, g.kv_index maps each query batch
+        # element to one of them, so the K/V projection runs once per distinct state (SPMM_models.py:137-198 pairs
+        # the same states with positives and hard negatives)
+        kvi = getattr(g, 'kv_index', None)
+        nkv = enc.shape[0] // g.Tk if kvi is not None else 0
+        K.attn_fwd(q, k, v, o, lse, g.B, W.heads, g.Tq, g.Tk, g.kv_len, g.causal, scale, p_attn, seed_a,
+                   kv_index=kvi, kv_batches=nkv)
         seed_h = next_seed() if p_hid > 0 else 0
         xsum = K.gemm(o, W.wo, M, H, H, bias=W.bo, residual=x, dropout_p=p_hid, seed=seed_h)
         y, mean, rstd = K.layernorm_fwd(xsum, W.ln_g, W.ln_b, W.eps, save_stats=need)
@@ -156,10 +162,14 @@ class _AttnBlock(torch.autograd.Function):
         Mk = enc.shape[0]
         k, v = kvbuf[:, :H], kvbuf[:, H:]
         dq = torch.empty_like(qkv)
-        dkv = torch.empty_like(kvbuf)
+        kvi = getattr(g, 'kv_index', None)
+        dkv = torch.empty_like(kvbuf) if kvi is None else torch.empty(g.B * g.Tk, 2 * H, device=x.device, dtype=BF16)
         K.attn_bwd(do, qkv, k, v, o, lse, dq, dkv[:, :H], dkv[:, H:], g.B, W.heads, g.Tq, g.Tk, g.kv_len, g.causal,
                    scale, p_attn, seed_a,
-                   dbias=None if W.g_bq is None else (W.g_bq, W.g_bkv[:H], W.g_bkv[H:]))
+                   dbias=None if W.g_bq is None else (W.g_bq, W.g_bkv[:H], W.g_bkv[H:]),
+                   kv_index=kvi, kv_batches=Mk // g.Tk if kvi is not None else 0)
+        if kvi is not None:                              # per-pair dK/dV -> the distinct states they were projected from
+            dkv = K.segment_sum_rows(dkv.view(g.B, g.Tk * 2 * H), kvi, Mk // g.Tk).view(Mk, 2 * H)
         _wgrad(dq, x, W.g_wq, H, H, M)
         dx = K.gemm(dq, W.wq, M, H, H, b_mn=True, residual=dxs)
         _wgrad(dkv, enc, W.g_wkv, 2 * H, H, Mk)
@@ -349,9 +359,7 @@ class _GatherRows(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         (idx,) = ctx.saved_tensors
-        dsrc = torch.zeros(ctx.shape, device=dout.device, dtype=dout.dtype)
-        K.scatter_add_rows(dsrc, idx, dout.contiguous())
-        return dsrc, None
+        return K.segment_sum_rows(dout.contiguous(), idx, ctx.shape[0]), None
 
 
 def gather_rows(src, idx):

@@ -247,9 +247,11 @@ class BertModel(nn.Module):
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
                 inputs_embeds=None, encoder_embeds=None, encoder_hidden_states=None, encoder_attention_mask=None,
                 past_key_values=None, use_cache=None, output_attentions=None, output_hidden_states=None,
-                return_dict=True, is_decoder=False, mode='multi_modal', causal_from=None):
+                return_dict=True, is_decoder=False, mode='multi_modal', causal_from=None, encoder_index=None):
         """`causal_from` (SPMM.forward only): the batch holds two passes over the same weights - rows [0, causal_from)
-        attend bidirectionally, rows [causal_from, B) causally - so both share every GEMM / LayerNorm launch."""
+        attend bidirectionally, rows [causal_from, B) causally - so both share every GEMM / LayerNorm launch.
+        `encoder_index` (int32 [B] on the device, SPMM.forward only): `encoder_hidden_states` holds DISTINCT states and
+        query batch element b cross-attends to states[encoder_index[b]] (`encoder_attention_mask` stays per b)."""
         if past_key_values is not None or output_attentions or output_hidden_states or head_mask is not None:
             raise NotImplementedError("unused on the SPMM hot path")
         cfg = self.config
@@ -285,11 +287,12 @@ class BertModel(nn.Module):
             if isinstance(encoder_hidden_states, (list, tuple)):
                 raise NotImplementedError("list-valued encoder_hidden_states is unused by the SPMM scripts")
             Be, Te = encoder_hidden_states.shape[:2]
-            if Be != B:
+            if Be != B and encoder_index is None:
                 raise ValueError("encoder batch %d != query batch %d" % (Be, B))
             enc = encoder_hidden_states.contiguous().view(Be * Te, -1)
             cmask = MaskInfo.of(encoder_attention_mask)
-            cross_geom = SimpleNamespace(B=B, Tq=T, Tk=Te, kv_len=None if cmask is None else cmask.kv_len, causal=False)
+            cross_geom = SimpleNamespace(B=B, Tq=T, Tk=Te, kv_len=None if cmask is None else cmask.kv_len, causal=False,
+                                         kv_index=encoder_index)
         fl, nl = cfg.fusion_layer, cfg.num_hidden_layers
         lo, hi = {'text': (0, fl), 'fusion': (fl, nl), 'multi_modal': (0, nl)}[mode]
         ov = _OVERLAP[0]

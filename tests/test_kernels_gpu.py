@@ -71,8 +71,28 @@ def test_colsum_gather_scatter_add():
     K.scatter_add_rows(dst, idx, src)
     ref = torch.zeros(12, 54, 128, device=DEV).index_add_(0, idx.long(), src.float())
     assert rel_err(dst, ref) < 1e-2
+    assert rel_err(K.segment_sum_rows(src, idx, 12), ref) < 4e-3
     a, b = rnd(4096, dtype=BF), rnd(4096, seed=9, dtype=BF)
     assert torch.equal(K.add_(a.clone(), b), (a.float() + b.float()).to(BF))
+
+
+@pytest.mark.parametrize("n_dst,n_idx,row", [(12, 12, 54 * 128), (96, 384, 64 * 1536), (96, 384, 54 * 1536), (5, 40, 8),
+                                             (7, 1, 4096)])
+def test_segment_sum_rows(n_dst, n_idx, row):
+    """out[t] = sum of the source rows mapped to t: exact fp32 sum rounded once; rows nobody maps to are zero."""
+    g = torch.Generator().manual_seed(n_idx)
+    idx = torch.randint(0, n_dst, (n_idx,), generator=g).int()
+    if n_dst > 2:
+        idx[idx == 2] = 0                          # destination 2 stays empty, destination 0 is crowded
+    idx = idx.to(DEV)
+    src = rnd(n_idx, row, dtype=BF, seed=3)
+    got = K.segment_sum_rows(src, idx, n_dst)
+    want = torch.zeros(n_dst, row, device=DEV, dtype=torch.float64).index_add_(0, idx.long(), src.double())
+    assert got.shape == (n_dst, row)
+    assert float((got.double() - want).abs().max()) <= 2 ** -8 * float(want.abs().max()) + 1e-6
+    if n_dst > 2:
+        assert float(got[2].abs().max()) == 0.0
+    assert torch.equal(got, K.segment_sum_rows(src, idx, n_dst))       # fixed summation order
 
 
 # ---------------------------------------------------------------- GEMM
@@ -364,6 +384,32 @@ def test_attention_causal_from_a_batch_index(B, first_causal, T):
         K.attn_bwd(do[r], q[r], k[r], v[r], o2[r], lse2[lo * h * T:hi * h * T], dqkv2[r, :H], dqkv2[r, H:2 * H], dqkv2[r, 2 * H:],
                    hi - lo, h, T, T, kv_len[lo:hi].contiguous(), flag, 0.125)
     assert torch.equal(o, o2) and torch.equal(lse, lse2) and torch.equal(dqkv, dqkv2)
+
+
+@pytest.mark.parametrize("B,nkv,Tq,Tk", [(8, 3, 54, 64), (384, 96, 54, 64), (384, 96, 64, 54), (6, 4, 99, 83), (5, 5, 17, 128)])
+def test_attention_shared_key_value_states(B, nkv, Tq, Tk):
+    """`kv_index`: batch element b reads the K/V rows of state kv_index[b]; identical, bit for bit, to materialising the
+    gathered K/V (what the ITM pass of the reference does with its cat'ed encoder states, SPMM_models.py:180-198)."""
+    h, H = 12, 768
+    q = rnd(B * Tq, H, dtype=BF, seed=21)
+    kvu = rnd(nkv * Tk, 2 * H, dtype=BF, seed=22)
+    idx = torch.randint(0, nkv, (B,), generator=torch.Generator().manual_seed(23)).int().to(DEV)
+    kv_len = torch.randint(Tk // 3, Tk + 1, (B,), generator=torch.Generator().manual_seed(24)).int().to(DEV)
+    kvg = kvu.view(nkv, Tk * 2 * H)[idx.long()].view(B * Tk, 2 * H).contiguous()
+    do = rnd(B * Tq, H, dtype=BF, seed=25)
+    res = []
+    for kv, kw in ((kvu, dict(kv_index=idx, kv_batches=nkv)), (kvg, {})):
+        o = torch.empty(B * Tq, H, device=DEV, dtype=BF)
+        lse = torch.empty(B * h * Tq, device=DEV)
+        K.attn_fwd(q, kv[:, :H], kv[:, H:], o, lse, B, h, Tq, Tk, kv_len, 0, 0.125, **kw)
+        dq = torch.zeros(B * Tq, H, device=DEV, dtype=BF)
+        dkv = torch.zeros(B * Tk, 2 * H, device=DEV, dtype=BF)
+        db = torch.zeros(3, H, device=DEV)
+        K.attn_bwd(do, q, kv[:, :H], kv[:, H:], o, lse, dq, dkv[:, :H], dkv[:, H:], B, h, Tq, Tk, kv_len, 0, 0.125,
+                   dbias=(db[0], db[1], db[2]), **kw)
+        res.append((o, lse, dq, dkv))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("B,h,Tq,Tk,causal", [(3, 12, 64, 64, False), (2, 4, 54, 99, False), (2, 12, 99, 99, True)])
