@@ -34,7 +34,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 CFG = os.path.join(REPO, "spmm_b200", "configs")
 H, I, E, P_TOK, V = 768, 3072, 256, 54, 300
-GEMM_DRAM_BYTES_PER_LAUNCH = 51.24e6   # profiles/r2_launches_dram.csv.gz: 86 192 MB over the 1682 gemm2 launches of two eager steps (ncu, cold caches)
+GEMM_DRAM_BYTES_PER_LAUNCH = 106.98e6   # profiles/r2_launches_dram.csv.gz: 106 336 MB over the 994 gemm2 launches of two eager steps (ncu, cold caches)
 
 
 def flops_per_molecule(l, B, Q):
