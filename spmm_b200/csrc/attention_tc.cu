@@ -448,7 +448,10 @@ int attn_fwd_tc_launch(const void* q, int ldq, const void* k, int ldk, const voi
 //   dQ = dS K           A = dS (K-major)    B = K  (MN-major)
 // with Pd = P o dropout-mask / keep, D_i = sum_j Pd_ij dP_ij, dS = P o (dP o mask / keep - D) * scale.
 // 576 threads: TMA producer (2-stage Q/K/V/dO ring), MMA issuer, 16 softmax warps = 4 threads per tile row (each
-// owns 32 key columns).  dQ / dK / dV leave through 3-D bulk tensor stores (rows beyond the sequence are clipped).
+// owns 16 key columns of the row's head when two heads share the tile, 32 otherwise; with 576 threads the register
+// file gives 96 per thread, and the 32-column form of the pair case spilled to local memory: 7.4 -> 4.6 us per tile).
+// dQ / dK / dV leave through 3-D bulk tensor stores (rows beyond the sequence are clipped), one issued by each of six
+// threads; their column sums (projection bias gradients) are kept in registers per head pair and flushed once.
 namespace spmm {
 
 constexpr int AB_STAGE_BYTES = 4 * AT_TILE_BYTES;            // Q, K, V, dO
@@ -459,6 +462,22 @@ constexpr int AB_SMEM = 1024 + AB_STAGES * AB_STAGE_BYTES + AB_PDS_BYTES + AB_XC
 constexpr uint32_t AB_S = 0, AB_DP = 128, AB_DK = 256, AB_DV = 320, AB_DQ = 384;   // TMEM columns
 
 struct AttnBwdMaps { CUtensorMap q, k, v, dout, dq, dk, dv; };
+
+template <int N> struct TmemLd;
+template <> struct TmemLd<32> {
+  static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+};
+template <> struct TmemLd<16> {
+  static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+  }
+};
 
 struct AttnBwdArgs {
   const float* lse;
@@ -475,12 +494,25 @@ struct AttnBwdArgs {
   float* dbq;   // optional [heads*64] fp32 each: += column sums of dQ / dK / dV (bias gradients of the q/k/v projections)
   float* dbk;
   float* dbv;
+  unsigned long long* trace;   // debug: 32 x u64 %globaltimer stamps per CTA, null in production
 };
 
+__device__ __forceinline__ void ab_mark(const AttnBwdArgs& a, int slot) {
+  if (a.trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[(size_t)blockIdx.x * 32 + slot] = t;
+  }
+}
+
+// PAIR: two heads of one batch element share a tile (Tq, Tk <= 64; every benchmarked shape): a row has 64 live key
+// columns, split 16 per softmax thread so all 16 warps work and nothing spills.  !PAIR: 128 columns, 32 per thread.
+template <bool PAIR>
 __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   pdl_trigger();
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  if (threadIdx.x == 0) ab_mark(a, 0);
   uint8_t* sPd = smem + AB_STAGES * AB_STAGE_BYTES;          // [2 chunks][128 rows][128 B]
   uint8_t* sdS = sPd + 2 * AT_TILE_BYTES;
   float* xch = reinterpret_cast<float*>(sPd + AB_PDS_BYTES);
@@ -514,7 +546,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
 
   // forward-compatible tile decoding (same pairing as attn_fwd_tc_kernel); K/V rows are batch-major (no broadcast)
   auto decode = [&](int tile, int& b, int& h0, int& h1, int& qrow0, int& qrow1, int& krow0, int& krow1) {
-    if (a.pair) {
+    if (PAIR) {
       b = tile / a.hp; h0 = 2 * (tile % a.hp); h1 = min(h0 + 1, a.heads - 1);
       qrow0 = qrow1 = b * a.Tq; krow0 = krow1 = (a.kv_index ? __ldg(a.kv_index + b) : b) * a.Tk;
     } else {
@@ -584,28 +616,33 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
       tc_commit(&empty[st]);
     }
   } else if (warp >= 2) {
-    // ===================== softmax-backward threads: 4 per tile row, 32 key columns each =====================
+    // ===================== softmax-backward threads: 4 per tile row =====================
     const int sw = warp - 2;
     const int part = sw >> 2, q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t drop_key = a.thresh16 ? fold_seed(salted(a.seed, a.salt)) : 0u;
     const float c2 = a.scale * AT_LOG2E;
-    const int slot = a.pair ? (r >> 6) : 0;
-    const int i = a.pair ? (r & 63) : r;
-    const int col0 = a.pair ? 64 * slot : 0;
-    const int ncol = a.pair ? 64 : 128;
-    const int cc = 32 * part - col0;                       // first key (within the head) of this thread's chunk
-    const bool mine = cc >= 0 && cc < ncol;                // warp-uniform
+    constexpr int NC = PAIR ? 16 : 32;                     // key columns per softmax thread
+    constexpr int NU = NC / 8;                             // = 16-byte units of a bf16 operand row
+    const int slot = PAIR ? (r >> 6) : 0;
+    const int i = PAIR ? (r & 63) : r;
+    const int cc = NC * part;                              // first key (within the head) of this thread's chunk
+    const uint32_t tcol = (PAIR ? 64 * slot : 0) + cc;     // its column in the S / dP accumulators
     const bool elected = (sw == 0 && lane == 0);
-    uint8_t* pd_row = sPd + (part >> 1) * AT_TILE_BYTES + r * 128;
-    uint8_t* ds_row = sdS + (part >> 1) * AT_TILE_BYTES + r * 128;
-    const int u0 = (part & 1) * 4;
+    const int st_role = (lane == 0 && sw < 6) ? sw : -1;   // issues (and waits for) one of the six output stores
+    float bsum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};       // PAIR: bias-gradient column sums per head pair
+    // operand rows: PAIR -> the head's own 64-key chunk (and zeros into the other head's chunk: the tile is block
+    // diagonal); !PAIR -> chunk = 64-key half of the row
+    const int chunk = PAIR ? slot : (part >> 1);
+    const int u0 = PAIR ? 2 * part : (part & 1) * 4;
+    uint8_t* pd_row = sPd + chunk * AT_TILE_BYTES + r * 128;
+    uint8_t* ds_row = sdS + chunk * AT_TILE_BYTES + r * 128;
     int n = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++n) {
       int b, h0, h1, q0r, q1r, k0r, k1r;
       decode(tile, b, h0, h1, q0r, q1r, k0r, k1r);
-      const int h = a.pair ? h0 + slot : h0;
+      const int h = PAIR ? h0 + slot : h0;
       const bool head_ok = h < a.heads;
       const bool valid = head_ok && (i < a.Tq);
       const int klen = a.kv_len ? min(__ldg(a.kv_len + b), a.Tk) : a.Tk;
@@ -613,27 +650,29 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
       const int bh = b * a.heads + h;
       const float lse2 = valid ? __ldg(a.lse + (size_t)bh * a.Tq + i) * AT_LOG2E : 0.f;
       const uint32_t ph = n & 1;
+      const bool tr = elected && a.trace != nullptr && n >= 1 && n < 4;   // tiles 1..3: steady state
+      const int tb = 4 + 8 * (n - 1);
       mbar_wait(sdp_full, ph);
       tc_fence_after();
-      float p[32], dpk[32];
+      if (tr) ab_mark(a, tb);
+      float p[NC], dpk[NC];
       float dpart = 0.f;
-      uint32_t kmask = 0xFFFFFFFFu;                        // dropout keep bits of this thread's 32 keys
-      const bool blk = mine && cc < klen;                  // warp-uniform
+      uint32_t kmask = 0xFFFFFFFFu;                        // dropout keep bits of this thread's keys
+      const bool blk = cc < klen;                          // warp-uniform
       if (blk) {
-        uint32_t sr[32], dr[32];
-        tmem_ld32(lane_addr + AB_S + 32 * part, sr);
-        tmem_ld32(lane_addr + AB_DP + 32 * part, dr);
+        uint32_t sr[NC], dr[NC];
+        TmemLd<NC>::ld(lane_addr + AB_S + tcol, sr);
+        TmemLd<NC>::ld(lane_addr + AB_DP + tcol, dr);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < NC; ++j) {
           p[j] = (valid && cc + j < jmax) ? at_exp2(__uint_as_float(sr[j]) * c2 - lse2) : 0.f;
           dpk[j] = __uint_as_float(dr[j]);
         }
         if (a.thresh16) {
-#pragma unroll
           kmask = 0u;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
+          for (int j = 0; j < NC; j += 2) {
             const uint32_t hb = at_drop_bits(drop_key, bh, i, cc + j);
             const bool k0 = (hb & 0xFFFFu) >= a.thresh16, k1 = (hb >> 16) >= a.thresh16;
             kmask |= (k0 ? 1u : 0u) << j;
@@ -643,22 +682,43 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
           }
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dpart += p[j] * dpk[j];     // = Pd_ij dP_ij (keep factor already in dpk)
+        for (int j = 0; j < NC; ++j) dpart += p[j] * dpk[j];     // = Pd_ij dP_ij (keep factor already in dpk)
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { p[j] = 0.f; dpk[j] = 0.f; }
+        for (int j = 0; j < NC; ++j) { p[j] = 0.f; dpk[j] = 0.f; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sdp_free);
+      if (PAIR) {                                          // S and dP are consumed: the next tile's may be issued
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sdp_free);
+      }
       xch[r * 4 + part] = dpart;
       // the Pd / dS tiles double as the output staging of the previous tile: wait until its bulk stores have read them
-      if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (st_role >= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       bar_sync_at(1, 512);
+      if (tr) ab_mark(a, tb + 1);
       const float D = (xch[r * 4] + xch[r * 4 + 1]) + (xch[r * 4 + 2] + xch[r * 4 + 3]);
+      if (!PAIR) {
+        // 32 columns per thread: p[] and dP together do not fit the register budget of 576 threads, so dP is read from
+        // TMEM a second time here instead of being carried across the barrier
+        if (blk) {
+          uint32_t dr[NC];
+          TmemLd<NC>::ld(lane_addr + AB_DP + tcol, dr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < NC; ++j)
+            dpk[j] = a.thresh16 ? (((kmask >> j) & 1u) ? __uint_as_float(dr[j]) * a.inv_keep : 0.f) : __uint_as_float(dr[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < NC; ++j) dpk[j] = 0.f;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sdp_free);
+      }
       // Pd = p * keep (keep = mask / keep_prob, bits kept in kmask)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         uint32_t wp[4], wd[4];
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
@@ -668,102 +728,123 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
           wp[e2] = pack_bf16x2(p[j] * k0f, p[j + 1] * k1f);
           wd[e2] = pack_bf16x2(p[j] * (dpk[j] - D) * a.scale, p[j + 1] * (dpk[j + 1] - D) * a.scale);
         }
-        *reinterpret_cast<uint4*>(pd_row + (((u0 + u) ^ (r & 7)) << 4)) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-        *reinterpret_cast<uint4*>(ds_row + (((u0 + u) ^ (r & 7)) << 4)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        const int off = ((u0 + u) ^ (r & 7)) << 4;
+        *reinterpret_cast<uint4*>(pd_row + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+        *reinterpret_cast<uint4*>(ds_row + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        if (PAIR) {   // the other head's keys: zero (rewritten every tile - the region doubles as output staging)
+          const int zoff = (1 - 2 * slot) * AT_TILE_BYTES + off;
+          *reinterpret_cast<uint4*>(pd_row + zoff) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(ds_row + zoff) = make_uint4(0u, 0u, 0u, 0u);
+        }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      // ---- outputs: part 0/1 -> dQ and dV column halves, part 2/3 -> dK column halves (lanes = query / key rows)
+      if (tr) ab_mark(a, tb + 2);
+      // ---- outputs (lanes = query rows of dQ / key rows of dK, dV)
       mbar_wait(out_full, ph);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
-      if (part < 2) {
-        tmem_ld32(lane_addr + AB_DQ + 32 * part, o0);
-        tmem_ld32(lane_addr + AB_DV + 32 * part, o1);
-      } else {
-        tmem_ld32(lane_addr + AB_DK + 32 * (part - 2), o0);
+      if (tr) ab_mark(a, tb + 3);
+      // dQ | dK | dV are 3 x 64 fp32 columns = twelve 16-column blocks, three per thread of a row (part p takes blocks
+      // 3p .. 3p+2): 48 live registers and the same work for every warp
+      uint32_t o[3][16];
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int g = 3 * part + t, which = g >> 2, cb = g & 3;
+        TmemLd<16>::ld(lane_addr + (which == 0 ? AB_DQ : (which == 1 ? AB_DK : AB_DV)) + 16 * cb, o[t]);
       }
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_free);
+      if (tr) ab_mark(a, tb + 4);
       // staging tiles ([128 rows][128 B], swizzled) in the Pd / dS region (the MMAs that read it are complete): dQ | dK | dV
-      {
-        uint8_t* t0 = sPd + (part < 2 ? 0 : AT_TILE_BYTES) + r * 128;
-        const int uu = (part & 1) * 4;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+      for (int t = 0; t < 3; ++t) {
+        const int g = 3 * part + t, which = g >> 2, cb = g & 3;
+        uint8_t* trow = sPd + which * AT_TILE_BYTES + r * 128;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
           uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o0[8 * u]), __uint_as_float(o0[8 * u + 1]));
-          w.y = pack_bf16x2(__uint_as_float(o0[8 * u + 2]), __uint_as_float(o0[8 * u + 3]));
-          w.z = pack_bf16x2(__uint_as_float(o0[8 * u + 4]), __uint_as_float(o0[8 * u + 5]));
-          w.w = pack_bf16x2(__uint_as_float(o0[8 * u + 6]), __uint_as_float(o0[8 * u + 7]));
-          *reinterpret_cast<uint4*>(t0 + (((uu + u) ^ (r & 7)) << 4)) = w;
-        }
-        if (part < 2) {
-          uint8_t* t1 = sPd + 2 * AT_TILE_BYTES + r * 128;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(o1[8 * u]), __uint_as_float(o1[8 * u + 1]));
-            w.y = pack_bf16x2(__uint_as_float(o1[8 * u + 2]), __uint_as_float(o1[8 * u + 3]));
-            w.z = pack_bf16x2(__uint_as_float(o1[8 * u + 4]), __uint_as_float(o1[8 * u + 5]));
-            w.w = pack_bf16x2(__uint_as_float(o1[8 * u + 6]), __uint_as_float(o1[8 * u + 7]));
-            *reinterpret_cast<uint4*>(t1 + (((uu + u) ^ (r & 7)) << 4)) = w;
-          }
+          w.x = pack_bf16x2(__uint_as_float(o[t][8 * u]), __uint_as_float(o[t][8 * u + 1]));
+          w.y = pack_bf16x2(__uint_as_float(o[t][8 * u + 2]), __uint_as_float(o[t][8 * u + 3]));
+          w.z = pack_bf16x2(__uint_as_float(o[t][8 * u + 4]), __uint_as_float(o[t][8 * u + 5]));
+          w.w = pack_bf16x2(__uint_as_float(o[t][8 * u + 6]), __uint_as_float(o[t][8 * u + 7]));
+          *reinterpret_cast<uint4*>(trow + (((2 * cb + u) ^ (r & 7)) << 4)) = w;
         }
       }
       fence_proxy_async();
       bar_sync_at(1, 512);
-      if (a.dbq != nullptr && sw < 12) {
-        // Bias gradients of the q/k/v projections = column sums of dQ / dK / dV (reference: autograd of nn.Linear,
-        // xbert.py:280-298), taken from the staged bf16 tiles instead of a separate pass over the stored tensors.
-        // Thread = (tensor, 64-row slot, column); rows past the sequence hold zeros (their P / dS rows are zero).
-        const int t = threadIdx.x - 64;
-        const int which = t >> 7, s_ = (t >> 6) & 1, c = t & 63;
-        const int hh = a.pair ? h0 + s_ : h0;
-        if (hh < a.heads) {
-          const uint8_t* base = sPd + which * AT_TILE_BYTES + (s_ * 64) * 128 + (c & 7) * 2;
-          const int u = c >> 3;
-          float acc = 0.f;
-#pragma unroll 8
-          for (int rr = 0; rr < 64; ++rr)
-            acc += bf2f(*reinterpret_cast<const __nv_bfloat16*>(base + rr * 128 + ((u ^ (rr & 7)) << 4)));
-          float* dst = which == 0 ? a.dbq : (which == 1 ? a.dbk : a.dbv);
-          atomicAdd(dst + hh * 64 + c, acc);
-        }
-      }
-      if (elected) {
-        uint8_t* sdq = sPd;
-        uint8_t* sdk = sPd + AT_TILE_BYTES;
-        uint8_t* sdv = sPd + 2 * AT_TILE_BYTES;
-        if (a.pair) {
-          at_tma_store_3d(&maps.dq, sdq, h0 * 64, 0, b);
-          at_tma_store_3d(&maps.dk, sdk, h0 * 64, 0, b);
-          at_tma_store_3d(&maps.dv, sdv, h0 * 64, 0, b);
-          if (h0 + 1 < a.heads) {
-            at_tma_store_3d(&maps.dq, sdq + AT_TILE_BYTES / 2, (h0 + 1) * 64, 0, b);
-            at_tma_store_3d(&maps.dk, sdk + AT_TILE_BYTES / 2, (h0 + 1) * 64, 0, b);
-            at_tma_store_3d(&maps.dv, sdv + AT_TILE_BYTES / 2, (h0 + 1) * 64, 0, b);
-          }
-        } else {
-          at_tma_store_3d(&maps.dq, sdq, h0 * 64, 0, b);
-          at_tma_store_3d(&maps.dk, sdk, h0 * 64, 0, b);
-          at_tma_store_3d(&maps.dv, sdv, h0 * 64, 0, b);
-          if (a.Tq > 64) at_tma_store_3d(&maps.dq, sdq + AT_TILE_BYTES / 2, h0 * 64, 64, b);
-          if (a.Tk > 64) {
-            at_tma_store_3d(&maps.dk, sdk + AT_TILE_BYTES / 2, h0 * 64, 64, b);
-            at_tma_store_3d(&maps.dv, sdv + AT_TILE_BYTES / 2, h0 * 64, 64, b);
-          }
+      if (tr) ab_mark(a, tb + 5);
+      // ---- bulk tensor stores of the staged tiles: six threads (lane 0 of warps sw 0..5) issue one each
+      if (st_role >= 0) {
+        const int which = st_role % 3, second = st_role / 3;            // dQ | dK | dV; first / second 64-row half
+        const CUtensorMap* mp = which == 0 ? &maps.dq : (which == 1 ? &maps.dk : &maps.dv);
+        const uint8_t* src = sPd + which * AT_TILE_BYTES + second * (AT_TILE_BYTES / 2);
+        if (PAIR) {                                                     // halves = the two heads of the pair
+          if (!second || h0 + 1 < a.heads) at_tma_store_3d(mp, src, (h0 + second) * 64, 0, b);
+        } else {                                                        // halves = rows 0..63 / 64..127 of one head
+          if (!second || (which == 0 ? a.Tq : a.Tk) > 64) at_tma_store_3d(mp, src, h0 * 64, 64 * second, b);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+      if (tr) ab_mark(a, tb + 6);
+      if (a.dbq != nullptr && sw < 12) {
+        // Bias gradients of the q/k/v projections = column sums of dQ / dK / dV (reference: autograd of nn.Linear,
+        // xbert.py:280-298), taken from the staged bf16 tiles instead of a separate pass over the stored tensors.
+        // Warp = (tensor, 64-row slot, 32-column half); lane = (16-byte unit, row group): 8 conflict-free 16-byte
+        // loads per lane, then the 8 row groups are folded by three exchanges that leave lane rg with column rg of
+        // its unit.  Rows past the sequence hold zeros (their P / dS rows are zero).
+        const int which = sw >> 2, s_ = (sw >> 1) & 1;
+        const int un = (sw & 1) * 4 + (lane >> 3), rg = lane & 7;
+        const uint8_t* base = sPd + which * AT_TILE_BYTES + (s_ * 64) * 128;
+        float c8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int rr = rg + 8 * k;
+          const uint4 w = *reinterpret_cast<const uint4*>(base + rr * 128 + ((un ^ (rr & 7)) << 4));
+          float x, y;
+          unpack_bf16x2(w.x, x, y); c8[0] += x; c8[1] += y;
+          unpack_bf16x2(w.y, x, y); c8[2] += x; c8[3] += y;
+          unpack_bf16x2(w.z, x, y); c8[4] += x; c8[5] += y;
+          unpack_bf16x2(w.w, x, y); c8[6] += x; c8[7] += y;
+        }
+        float d4[4], d2[2];
+        const bool b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          d4[j] = (b4 ? c8[j + 4] : c8[j]) + __shfl_xor_sync(0xFFFFFFFFu, b4 ? c8[j] : c8[j + 4], 4);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          d2[j] = (b2 ? d4[j + 2] : d4[j]) + __shfl_xor_sync(0xFFFFFFFFu, b2 ? d4[j] : d4[j + 2], 2);
+        const float csum = (b1 ? d2[1] : d2[0]) + __shfl_xor_sync(0xFFFFFFFFu, b1 ? d2[0] : d2[1], 1);
+        if (PAIR && a.hp <= 6) {
+          // per-head-pair register accumulators, flushed once when the CTA is done: no per-tile atomics
+          const int hpi = h0 >> 1;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) bsum[k] += (hpi == k) ? csum : 0.f;
+        } else {
+          const int hh = PAIR ? h0 + s_ : h0;
+          float* dst = which == 0 ? a.dbq : (which == 1 ? a.dbk : a.dbv);
+          if (hh < a.heads) atomicAdd(dst + hh * 64 + un * 8 + rg, csum);
+        }
+      }
+      if (tr) ab_mark(a, tb + 7);
     }
-    if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (st_role >= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (PAIR && a.hp <= 6 && a.dbq != nullptr && sw < 12) {
+      const int which = sw >> 2, s_ = (sw >> 1) & 1, c = ((sw & 1) * 4 + (lane >> 3)) * 8 + (lane & 7);
+      float* dst = which == 0 ? a.dbq : (which == 1 ? a.dbk : a.dbv);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int hh = 2 * k + s_;
+        if (k < a.hp && hh < a.heads) atomicAdd(dst + hh * 64 + c, bsum[k]);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) ab_mark(a, 3);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -798,14 +879,18 @@ int attn_bwd_tc_launch(const void* d_o, int lddo, const void* q, int ldq, const 
   a.hp = (heads + 1) / 2;
   a.num_tiles = a.pair ? batch * a.hp : batch * heads;
   a.dbq = dbq; a.dbk = dbk; a.dbv = dbv; a.kv_index = kv_index;
+  a.trace = g_attn_trace;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   const int ctas = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
-  cudaError_t le = launch_pdl(attn_bwd_tc_kernel, dim3(ctas), dim3(AT_THREADS), AB_SMEM, st, maps, a);
+  cudaError_t le = a.pair ? launch_pdl(attn_bwd_tc_kernel<true>, dim3(ctas), dim3(AT_THREADS), AB_SMEM, st, maps, a)
+                          : launch_pdl(attn_bwd_tc_kernel<false>, dim3(ctas), dim3(AT_THREADS), AB_SMEM, st, maps, a);
   if (le != cudaSuccess) return (int)le;
   return 0;
 }
