@@ -583,14 +583,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
     const uint32_t id_mm = umma_idesc_bf16(128, 64, 1, 1);    // dV, dK: A = [query][key] tile read MN-major, B MN-major
     const uint32_t id_km = umma_idesc_bf16(128, 64, 0, 1);    // dQ: A = dS K-major, B = K MN-major
     const uint32_t aPd = smem_u32(sPd), adS = smem_u32(sdS);
-    int n = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++n) {
-      const int st = n % AB_STAGES;
-      const uint32_t ph = n & 1;
+    // S and dP of tile m: issued as soon as the softmax threads have read tile m-1's, i.e. while they are still turning
+    // tile m-1's P / dP into the dS operand - the accumulators are ready when they come back for tile m
+    auto issue_sdp = [&](int m) {
+      const int st = m % AB_STAGES;
       const uint32_t sq = smem_u32(smem + st * AB_STAGE_BYTES), sk = sq + AT_TILE_BYTES, sv = sk + AT_TILE_BYTES,
                      sdo = sv + AT_TILE_BYTES;
-      mbar_wait(&full[st], (n / AB_STAGES) & 1);
-      mbar_wait(sdp_free, ph ^ 1);
+      mbar_wait(&full[st], (m / AB_STAGES) & 1);
+      mbar_wait(sdp_free, (m & 1) ^ 1);
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -599,6 +599,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
       for (int k = 0; k < 4; ++k)
         tc_mma_bf16(tmem_base + AB_DP, umma_smem_desc(sdo + k * 32, 16, 1024), umma_smem_desc(sv + k * 32, 16, 1024), id_kk, k != 0);
       tc_commit(sdp_full);
+    };
+    int n = 0;
+    if ((int)blockIdx.x < a.num_tiles) issue_sdp(0);
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++n) {
+      const int st = n % AB_STAGES;
+      const uint32_t ph = n & 1;
+      const uint32_t sq = smem_u32(smem + st * AB_STAGE_BYTES), sk = sq + AT_TILE_BYTES, sdo = sk + 2 * AT_TILE_BYTES;
+      if (tile + (int)gridDim.x < a.num_tiles) issue_sdp(n + 1);
       mbar_wait(pds_full, ph);
       mbar_wait(acc_free, ph ^ 1);
       tc_fence_after();
@@ -638,6 +646,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
     const int u0 = PAIR ? 2 * part : (part & 1) * 4;
     uint8_t* pd_row = sPd + chunk * AT_TILE_BYTES + r * 128;
     uint8_t* ds_row = sdS + chunk * AT_TILE_BYTES + r * 128;
+    // per-tile scalars from global memory (key count of the batch element, this row's log-sum-exp) are fetched one
+    // tile ahead: their latency would otherwise sit between two tiles
+    auto fetch = [&](int tile, int& klen_out, float& lse_out) {
+      int b, h0, h1, q0r, q1r, k0r, k1r;
+      decode(tile, b, h0, h1, q0r, q1r, k0r, k1r);
+      const int h = PAIR ? h0 + slot : h0;
+      klen_out = a.kv_len ? min(__ldg(a.kv_len + b), a.Tk) : a.Tk;
+      lse_out = (h < a.heads && i < a.Tq) ? __ldg(a.lse + (size_t)(b * a.heads + h) * a.Tq + i) : 0.f;
+    };
+    int klen_nx = 0;
+    float lse_nx = 0.f;
+    if ((int)blockIdx.x < a.num_tiles) fetch(blockIdx.x, klen_nx, lse_nx);
     int n = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++n) {
       int b, h0, h1, q0r, q1r, k0r, k1r;
@@ -645,10 +665,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_bwd_tc_kernel(const __grid
       const int h = PAIR ? h0 + slot : h0;
       const bool head_ok = h < a.heads;
       const bool valid = head_ok && (i < a.Tq);
-      const int klen = a.kv_len ? min(__ldg(a.kv_len + b), a.Tk) : a.Tk;
+      const int klen = klen_nx;
       const int jmax = (a.causal > 0 && b >= a.causal - 1) ? min(klen, i + 1) : klen;
       const int bh = b * a.heads + h;
-      const float lse2 = valid ? __ldg(a.lse + (size_t)bh * a.Tq + i) * AT_LOG2E : 0.f;
+      const float lse2 = lse_nx * AT_LOG2E;
+      if (tile + (int)gridDim.x < a.num_tiles) fetch(tile + gridDim.x, klen_nx, lse_nx);
       const uint32_t ph = n & 1;
       const bool tr = elected && a.trace != nullptr && n >= 1 && n < 4;   // tiles 1..3: steady state
       const int tb = 4 + 8 * (n - 1);

@@ -38,7 +38,7 @@ for (B, Tq, Tk, p) in [(96, 64, 64, 0.1), (96, 64, 64, 0.0), (288, 64, 54, 0.1)]
 bnames = {0: "entry", 3: "exit"}
 for n in range(3):
     for k, nm in enumerate(["S,dP ready", "P/D pass done (barrier)", "Pd,dS written", "dQ,dK,dV ready", "accumulators read",
-                            "staged (barrier)", "bias sums done", "stores issued"]):
+                            "staged (barrier)", "stores issued", "bias sums done"]):
         bnames[4 + 8 * n + k] = "tile%d %s" % (n + 1, nm)
 for (B, Tq, Tk, p, bias) in [(384, 64, 64, 0.1, True), (384, 64, 64, 0.1, False), (384, 54, 64, 0.1, True), (192, 54, 54, 0.1, True)]:
     H, h = 768, 12
