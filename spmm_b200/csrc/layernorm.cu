@@ -1,9 +1,11 @@
 // LayerNorm forward/backward over bf16 rows (reference: nn.LayerNorm sites xbert.py:184,366,444,670;
 // eps 1e-12; fp32 statistics as torch's autocast keeps LayerNorm in fp32).
-// Forward / backward-dx: one warp per row; a lane owns 16-byte chunks {lane, lane+32, ...} of the row, so a 768-wide
-// row is three fully coalesced 512-byte warp transactions.  Backward parameter gradients (dgamma, dbeta and the bias
-// gradient of the dense that feeds the residual branch) are a separate column-parallel reduction kernel.
-// HBM-bound: 4 B/element forward, 6-8 B/element for dx, 6 B/element for the parameter reduction.
+// Forward: one warp per row; a lane owns 16-byte chunks {lane, lane+32, ...} of the row, so a 768-wide row is three
+// fully coalesced 512-byte warp transactions.  Backward: ONE kernel (ln_bwd_fused_kernel) produces dx, the masked
+// branch gradient and the parameter / bias column sums from a single read of dy and x; the older pair (row-parallel dx
+// kernel + column-parallel parameter reduction) remains for H > 768 and for calls that want no parameter gradients
+// (SPMM_LN_BWD_SPLIT=1 forces it, for A/B timing).  HBM-bound by design: 4 B/element forward, 8-10 B/element backward.
+#include <cstdlib>
 #include "common.cuh"
 #include "spmm_b200.h"
 
@@ -224,6 +226,157 @@ ln_bwd_param_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
   }
 }
 
+// One pass over dy and x for BOTH results of the backward: a warp walks rows (stride = warps in the grid), writes dx
+// (and the dropout-masked branch gradient) of each, and keeps the column sums dgamma / dbeta / dbias of all its rows in
+// registers; they leave through a shared-memory fold per CTA and one atomicAdd per column and CTA.  The two-kernel form
+// read dy and x twice and the branch gradient once more (6 + 6..8 B/element); this one moves 4 B/element in, 2..4 out.
+// A warp's rows arrive through its own ring of LNF_STAGES shared-memory slots filled by cp.async (each lane copies and
+// later reads the same 16-byte chunks, so no cross-lane synchronisation is needed): with ~14 rows per warp and one row
+// in flight the kernel was bound by load latency (48 us for 24576 rows), not by HBM.
+constexpr int LNF_WARPS = 12;                            // 384 threads, one CTA per SM: ~170 registers per thread
+constexpr int LNF_STAGES = 4;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+template <int NCH>
+__global__ void __launch_bounds__(LNF_WARPS * 32, 1)
+ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_branch, float* dgamma, float* dbeta,
+                    float* dbias, int rows, int H, unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep,
+                    unsigned long long br_seed, uint32_t br_thresh, float br_inv_keep, const unsigned long long* salt) {
+  extern __shared__ uint4 ln_ring[];                     // [warp][stage][x | dy][NCH * 32] 16-byte chunks
+  pdl_trigger();
+  __shared__ float sh[3][NCH * 256];
+  for (int i = threadIdx.x; i < 3 * NCH * 256; i += LNF_WARPS * 32) (&sh[0][0])[i] = 0.f;
+  __syncthreads();
+  pdl_wait();
+  const uint32_t out_key = out_thresh ? fold_seed(salted(out_seed, salt)) : 0u;
+  const uint32_t br_key = br_thresh ? fold_seed(salted(br_seed, salt)) : 0u;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nw = gridDim.x * LNF_WARPS;
+  uint4* ring = ln_ring + (size_t)w * LNF_STAGES * 2 * NCH * 32;
+  auto issue = [&](int row, int slot) {
+    if (row < rows) {
+      uint4* dst = ring + (size_t)slot * 2 * NCH * 32;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col = (lane + 32 * c) * 8;
+        if (col < H) {
+          cp_async16(dst + lane + 32 * c, x + (size_t)row * H + col);
+          cp_async16(dst + NCH * 32 + lane + 32 * c, dy + (size_t)row * H + col);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float ag[NCH][8], ab[NCH][8], as[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[c][j] = ab[c][j] = as[c][j] = 0.f;
+  const int row0 = blockIdx.x * LNF_WARPS + w;
+#pragma unroll
+  for (int s = 0; s < LNF_STAGES - 1; ++s) issue(row0 + s * nw, s);
+  float mu_nx = row0 < rows ? __ldg(mean + row0) : 0.f, rs_nx = row0 < rows ? __ldg(rstd + row0) : 0.f;
+  int k = 0;
+  for (int row = row0; row < rows; row += nw, ++k) {
+    issue(row + (LNF_STAGES - 1) * nw, (k + LNF_STAGES - 1) % LNF_STAGES);
+    const float mu = mu_nx, rs = rs_nx;
+    if (row + nw < rows) { mu_nx = __ldg(mean + row + nw); rs_nx = __ldg(rstd + row + nw); }
+    asm volatile("cp.async.wait_group %0;" ::"n"(LNF_STAGES - 1) : "memory");
+    const uint4* src = ring + (size_t)(k % LNF_STAGES) * 2 * NCH * 32;
+    uint4 xr[NCH], dr[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      xr[c] = src[lane + 32 * c];
+      dr[c] = src[NCH * 32 + lane + 32 * c];
+    }
+    uint32_t keep = 0xFFFFFFFFu;                         // dropout of the forward output (embedding LayerNorm): bit per element
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (lane + 32 * c) * 8;
+      if (col < H) {
+        float xh[8], d[8], gm[8];
+        unpack_bf16x2(xr[c].x, xh[0], xh[1]); unpack_bf16x2(xr[c].y, xh[2], xh[3]);
+        unpack_bf16x2(xr[c].z, xh[4], xh[5]); unpack_bf16x2(xr[c].w, xh[6], xh[7]);
+        unpack_bf16x2(dr[c].x, d[0], d[1]); unpack_bf16x2(dr[c].y, d[2], d[3]);
+        unpack_bf16x2(dr[c].z, d[4], d[5]); unpack_bf16x2(dr[c].w, d[6], d[7]);
+        load8f(gamma + col, gm);
+        if (out_thresh) {  // forward applied dropout after the affine: dy_affine = dy * mask / keep
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const uint32_t hb = drop_bits2(out_key, (uint32_t)row * H + col + j);
+            const bool k0 = (hb & 0xFFFFu) >= out_thresh, k1 = (hb >> 16) >= out_thresh;
+            if (!k0) keep &= ~(1u << (8 * c + j));
+            if (!k1) keep &= ~(1u << (8 * c + j + 1));
+            d[j] = k0 ? d[j] * out_inv_keep : 0.f;
+            d[j + 1] = k1 ? d[j + 1] * out_inv_keep : 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xn = (xh[j] - mu) * rs;
+          const float g = d[j] * gm[j];
+          s1 += g;
+          s2 += g * xn;
+          ag[c][j] += d[j] * xn;
+          ab[c][j] += d[j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (lane + 32 * c) * 8;
+      if (col < H) {
+        float xh[8], d[8], gm[8], o[8];
+        unpack_bf16x2(xr[c].x, xh[0], xh[1]); unpack_bf16x2(xr[c].y, xh[2], xh[3]);
+        unpack_bf16x2(xr[c].z, xh[4], xh[5]); unpack_bf16x2(xr[c].w, xh[6], xh[7]);
+        unpack_bf16x2(dr[c].x, d[0], d[1]); unpack_bf16x2(dr[c].y, d[2], d[3]);
+        unpack_bf16x2(dr[c].z, d[4], d[5]); unpack_bf16x2(dr[c].w, d[6], d[7]);
+        load8f(gamma + col, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dj = out_thresh ? (((keep >> (8 * c + j)) & 1u) ? d[j] * out_inv_keep : 0.f) : d[j];
+          o[j] = rs * (dj * gm[j] - s1 - (xh[j] - mu) * rs * s2);
+        }
+        store8(dx + (size_t)row * H + col, o);
+        if (dx_branch) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) drop_pair(br_key, (uint32_t)row * H + col + j, br_thresh, br_inv_keep, o[j], o[j + 1]);
+          store8(dx_branch + (size_t)row * H + col, o);
+        }
+        if (dbias != nullptr) {
+          // the bias gradient of the dense is the column sum of the STORED (bf16) branch gradient, as autograd forms it
+#pragma unroll
+          for (int j = 0; j < 8; ++j) as[c][j] += bf2f(f2bf(o[j]));
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // fold the CTA's warps: element (c, j) of a lane lives at [j][lane + 32 c] so a warp's adds hit 32 different banks
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = j * (NCH * 32) + lane + 32 * c;
+      atomicAdd(&sh[0][idx], ag[c][j]);
+      atomicAdd(&sh[1][idx], ab[c][j]);
+      if (dbias != nullptr) atomicAdd(&sh[2][idx], as[c][j]);
+    }
+  __syncthreads();
+  for (int col = threadIdx.x; col < H; col += LNF_WARPS * 32) {
+    const int idx = (col & 7) * (NCH * 32) + (col >> 3);
+    if (dgamma) atomicAdd(dgamma + col, sh[0][idx]);
+    if (dbeta) atomicAdd(dbeta + col, sh[1][idx]);
+    if (dbias) atomicAdd(dbias + col, sh[2][idx]);
+  }
+}
+
 static inline void drop_params(float p, uint32_t& thresh, float& inv_keep) {
   thresh = p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u;
   inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
@@ -266,6 +419,28 @@ extern "C" int spmm_layernorm_bwd(const void* dy, const void* x, const float* me
   const int nch = (H + 255) / 256;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t le = cudaSuccess;
+  static const int split = [] { const char* e = getenv("SPMM_LN_BWD_SPLIT"); return e && e[0] == '1' ? 1 : 0; }();
+  if (!split && nch <= 3 && (dgamma || dbeta || dbias)) {
+    int ctas = (rows + LNF_WARPS - 1) / LNF_WARPS;
+    if (ctas > kNumSMs) ctas = kNumSMs;
+    static bool configured[4] = {false, false, false, false};
+#define SPMM_LN_BWDF(N)                                                                                                  \
+  do {                                                                                                                   \
+    constexpr int ring_bytes = LNF_WARPS * LNF_STAGES * 2 * N * 32 * 16;                                                 \
+    if (!configured[N]) {                                                                                                \
+      le = cudaFuncSetAttribute(ln_bwd_fused_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes);        \
+      configured[N] = le == cudaSuccess;                                                                                 \
+    }                                                                                                                    \
+    if (le == cudaSuccess)                                                                                               \
+      le = launch_pdl(ln_bwd_fused_kernel<N>, dim3(ctas), dim3(LNF_WARPS * 32), ring_bytes, st,                          \
+                      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx,          \
+                      (__nv_bfloat16*)dx_branch, dgamma, dbeta, dbias, rows, H, out_seed, oth, oik, branch_seed, bth,    \
+                      bik, spmm_g_rng_salt);                                                                             \
+  } while (0)
+    if (nch == 1) SPMM_LN_BWDF(1); else if (nch == 2) SPMM_LN_BWDF(2); else SPMM_LN_BWDF(3);
+#undef SPMM_LN_BWDF
+    return le != cudaSuccess ? (int)le : 0;
+  }
 #define SPMM_LN_BWD(N) le = launch_pdl(ln_bwd_dx_kernel<N>, dim3(grid), dim3(LN_WARPS * 32), 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_branch, rows, H, out_seed, oth, oik, branch_seed, bth, bik, spmm_g_rng_salt)
   if (nch == 1) SPMM_LN_BWD(1); else if (nch == 2) SPMM_LN_BWD(2); else if (nch == 3) SPMM_LN_BWD(3); else SPMM_LN_BWD(4);
 #undef SPMM_LN_BWD

@@ -95,7 +95,7 @@ def bench_attn():
 
 
 def bench_ln():
-    for rows in (6144, 5184, 12288):
+    for rows in (6144, 10368, 12288, 20736, 24576):
         H = 768
         x = torch.randn(rows, H, device=DEV).to(BF)
         g, b = torch.ones(H, device=DEV), torch.zeros(H, device=DEV)
