@@ -459,7 +459,7 @@ struct Gemm2Maps {
 
 // ---- epilogue chunk math (2-CTA kernel).  A thread owns one output row; a chunk is C = 16 consecutive columns of it.
 // Staging address of 16-byte unit u of row r in a box: box + r*128 + ((u ^ (r & 7)) << 4).
-enum { EPI_GENERIC = 0, EPI_GELU_GRAD = 1, EPI_DGELU_MUL = 2, EPI_LINEAR = 3 };
+enum { EPI_GENERIC = 0, EPI_GELU_GRAD = 1, EPI_DGELU_MUL = 2, EPI_LINEAR = 3, EPI_GELU = 4 };
 constexpr int EC = 16;              // columns per epilogue chunk
 constexpr int ENP = EC / 2;         // packed fp32 pairs per chunk
 constexpr int ESU = EC / 8;         // 16-byte units of a bf16 chunk
@@ -498,6 +498,17 @@ __device__ __forceinline__ void epi2_gelu_grad(f32x2 (&v)[ENP], const float* s_b
 #pragma unroll
   for (int j = 0; j < ENP; ++j) gelu_and_grad2(v[j], v[j], gr[j]);
   stage_units(pre_row, u0, sw, gr);
+  stage_units(out_row, u0, sw, v);
+}
+// FFN-up / LM-head transform without a backward (momentum encoders, inference): act = gelu(acc + bias), one output
+__device__ __forceinline__ void epi2_gelu(f32x2 (&v)[ENP], const float* s_bias_chunk, uint8_t* out_row, const int u0,
+                                          const int sw) {
+  add_bias2(v, s_bias_chunk);
+#pragma unroll
+  for (int j = 0; j < ENP; ++j) {
+    f32x2 unused;
+    gelu_and_grad2(v[j], v[j], unused);
+  }
   stage_units(out_row, u0, sw, v);
 }
 // FFN backward: d pre = (dY . W2) * gelu'(pre), the factor stored by the forward
@@ -774,6 +785,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
       if (ge && st && has_pre && !has_side && p.drop_thresh16 == 0 && p.bias != nullptr) mode = EPI_GELU_GRAD;
       else if (dg && st && !ge && !has_pre && p.bias == nullptr && p.drop_thresh16 == 0) mode = EPI_DGELU_MUL;
       else if (!ge && !dg && !has_pre) mode = EPI_LINEAR;
+      else if (ge && !dg && !has_pre && !has_side && p.drop_thresh16 == 0 && p.bias != nullptr) mode = EPI_GELU;
     }
     // The bf16 side operand (residual, or the stored gelu' factor) arrives by TMA in the output staging tile
     // (side_tma: single bf16 output) and is replaced in place by the result; with a 2nd output the staging tile has no
@@ -858,6 +870,7 @@ gemm2_bf16_kernel(const __grid_constant__ Gemm2Maps maps, const GemmParams p) {
             if (more) tmem_ld16(taddr + ct_next, rr);
             if (mode == EPI_GELU_GRAD) epi2_gelu_grad(v2, s_bias + ct, out_row, pre_row, u0, sw);
             else if (mode == EPI_DGELU_MUL) epi2_dgelu_mul(v2, side_cur, out_row, u0, sw);
+            else if (mode == EPI_GELU) epi2_gelu(v2, s_bias + ct, out_row, u0, sw);
             else epi2_linear(p, v2, s_bias + ct, m0 + r, col0, drop_key, has_side, side_cur, out_row, u0, sw);
           } else {
             float v[EC];

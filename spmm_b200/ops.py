@@ -107,8 +107,10 @@ def grad_ready(x, callback):
 # --------------------------------------------------------------------------------------------- attention block
 class _AttnBlock(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, enc, anchor, W, g, p_attn, p_hid):
-        need = any(ctx.needs_input_grad)
+    def forward(ctx, x, enc, anchor, W, g, p_attn, p_hid, grad_mode):
+        # needs_input_grad ignores torch.no_grad() (and grad mode is always off inside forward, so the caller passes
+        # it): the momentum passes must not write backward state (LSE, LayerNorm statistics, 2nd GELU-GEMM output)
+        need = grad_mode and any(ctx.needs_input_grad)
         M, H = x.shape
         scale = 1.0 / math.sqrt(H // W.heads)
         if enc is None:
@@ -158,7 +160,7 @@ class _AttnBlock(torch.autograd.Function):
                        dbias=None if gb is None else (gb[:H], gb[H:2 * H], gb[2 * H:]))
             _wgrad(dqkv, x, W.g_wqkv, 3 * H, H, M)
             dx = K.gemm(dqkv, W.wqkv, M, H, 3 * H, b_mn=True, residual=dxs)
-            return dx, None, None, None, None, None, None
+            return dx, None, None, None, None, None, None, None
         Mk = enc.shape[0]
         k, v = kvbuf[:, :H], kvbuf[:, H:]
         dq = torch.empty_like(qkv)
@@ -174,12 +176,12 @@ class _AttnBlock(torch.autograd.Function):
         dx = K.gemm(dq, W.wq, M, H, H, b_mn=True, residual=dxs)
         _wgrad(dkv, enc, W.g_wkv, 2 * H, H, Mk)
         denc = K.gemm(dkv, W.wkv, Mk, H, 2 * H, b_mn=True) if ctx.needs_input_grad[1] else None
-        return dx, denc, None, None, None, None, None
+        return dx, denc, None, None, None, None, None, None
 
 
 def attn_block(x, enc, W, geom, p_attn, p_hid, anchor):
     """LN(dropout(dense(attention(x, enc or x))) + x) on [tokens, H] bf16."""
-    return _AttnBlock.apply(x, enc, anchor, W, geom, p_attn, p_hid)
+    return _AttnBlock.apply(x, enc, anchor, W, geom, p_attn, p_hid, torch.is_grad_enabled())
 
 
 # --------------------------------------------------------------------------------------------- FFN block
@@ -188,8 +190,8 @@ _DGELU_STORED = os.environ.get("SPMM_DGELU_STORED", "1") != "0"
 
 class _FfnBlock(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, anchor, W, p_hid):
-        need = any(ctx.needs_input_grad)
+    def forward(ctx, x, anchor, W, p_hid, grad_mode):
+        need = grad_mode and any(ctx.needs_input_grad)
         M, H = x.shape
         I = W.w1.shape[0]
         pre = torch.empty(M, I, device=x.device, dtype=BF16) if need else None
@@ -217,12 +219,12 @@ class _FfnBlock(torch.autograd.Function):
         dpre = K.gemm(dxb, W.w2, M, I, H, b_mn=True, dgelu_pre=pre, dgelu_stored=_DGELU_STORED, colsum_out=W.g_b1)
         _wgrad(dpre, x, W.g_w1, I, H, M)
         dx = K.gemm(dpre, W.w1, M, H, I, b_mn=True, residual=dxs)
-        return dx, None, None, None
+        return dx, None, None, None, None
 
 
 def ffn_block(x, W, p_hid, anchor):
     """LN(dropout(dense2(gelu(dense1(x)))) + x)."""
-    return _FfnBlock.apply(x, anchor, W, p_hid)
+    return _FfnBlock.apply(x, anchor, W, p_hid, torch.is_grad_enabled())
 
 
 # --------------------------------------------------------------------------------------------- embeddings

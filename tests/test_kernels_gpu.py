@@ -202,6 +202,9 @@ def test_gemm_epilogues_multi_tile(M, N, K_):
     gstore = mk()
     act2 = K.gemm(a, w, M, N, K_, bias=bias, gelu=True, pre_act_out=gstore, out=mk(), dgelu_stored=True)
     assert rel_err(act2, F.gelu(ref_pre)) < 6e-3 and rel_err(gstore, xg.grad) < 6e-3
+    # single-output GELU (momentum encoders / inference: no backward state) is the same erf evaluation, bit for bit
+    act1 = K.gemm(a, w, M, N, K_, bias=bias, gelu=True, out=mk(), dgelu_stored=True)
+    assert torch.equal(act1, act2)
     out = K.gemm(a, w, M, N, K_, dgelu_pre=gstore, out=mk(), dgelu_stored=True)
     assert rel_err(out, (a.float() @ w.float().t()) * gstore.float()) < 6e-3
     # fp32 store and fp32 accumulate
