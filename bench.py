@@ -34,7 +34,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 CFG = os.path.join(REPO, "spmm_b200", "configs")
 H, I, E, P_TOK, V = 768, 3072, 256, 54, 300
-GEMM_DRAM_BYTES_PER_LAUNCH = 106.98e6   # profiles/r2_launches_dram.csv.gz: 106 336 MB over the 994 gemm2 launches of two eager steps (ncu, cold caches)
+GEMM_DRAM_BYTES_PER_LAUNCH = 105.33e6   # profiles/r2_launches_dram.csv.gz: 104 697 MB over the 994 gemm2 launches of two eager steps (ncu, cold caches)
 
 
 def flops_per_molecule(l, B, Q):
@@ -559,7 +559,6 @@ def kernel_rooflines(torch, kernels, model, step_fn, B, world, graph_args=None):
             "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
             "traffic": traffic, "launches": g_n, "ms_per_step_in_kernel": g_ms, "flops_per_step": g_fl, "how": how,
             "flops_per_launch": g_fl / max(g_n, 1), "avg_launch_us": 1e3 * g_ms / max(g_n, 1),
-            "event_timed_eager": {"achieved": ev_fl / (ev_ms / 1e3) / 1e12, "ms_per_step_in_kernel": ev_ms, "launches": ev_n},
             "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)"}
     if in_graph is not None and os.environ.get("SPMM_BENCH_GEMM_TABLE"):
         agg = {}
