@@ -270,6 +270,36 @@ def test_layernorm_fwd_bwd(rows, H):
     assert rel_err(dbias, dx.float().sum(0)) < 1e-3
 
 
+@pytest.mark.parametrize("rows", [1000, 20736])
+def test_layernorm_backward_branch_mask_is_the_gemm_epilogue_mask(rows):
+    """BertSelfOutput / BertOutput (xbert.py:369-373, 447-451): LN(dropout(dense(h)) + x).  The dense GEMM applies the
+    dropout mask in its epilogue; the LayerNorm backward re-creates it from (seed, row * N + col) for the gradient of
+    the dense branch and sums that gradient's columns for the dense bias - no mask tensor exists in between."""
+    H, Kd = 768, 256
+    a, w = rnd(rows, Kd, dtype=BF, seed=1), rnd(H, Kd, dtype=BF, seed=2, scale=0.1)
+    bias, res = rnd(H, seed=3), rnd(rows, H, dtype=BF, seed=4)
+    dense = K.gemm(a, w, rows, H, Kd, bias=bias)
+    xsum = K.gemm(a, w, rows, H, Kd, bias=bias, residual=res, dropout_p=0.1, seed=77)
+    kept = (xsum.float() - res.float()).abs() > 0.5 * dense.float().abs().clamp_min(1e-3)    # dropped elements equal the residual
+    kept = kept | (dense.float().abs() < 2e-2)                                                # undecidable where dense ~ 0
+    assert abs(float(kept.float().mean()) - 0.9) < 0.02
+    g, b = 1 + 0.1 * rnd(H, seed=5), 0.1 * rnd(H, seed=6)
+    y, mean, rstd = K.layernorm_fwd(xsum, g, b, 1e-12)
+    dy = rnd(rows, H, dtype=BF, seed=7)
+    dg, db, dbias = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    dx, dxb = K.layernorm_bwd(dy, xsum, mean, rstd, g, dg, db, dbias=dbias, want_branch=True, branch_dropout_p=0.1, branch_seed=77)
+    xf = xsum.float().requires_grad_(True)
+    gf, bf = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    F.layer_norm(xf, (H,), gf, bf, 1e-12).backward(dy.float())
+    assert rel_err(dx, xf.grad) < 6e-3
+    assert rel_err(dg, gf.grad) < 2e-3 and rel_err(db, bf.grad) < 2e-3
+    sure = dense.float().abs() >= 2e-2
+    want = torch.where(kept, dx.float() / 0.9, torch.zeros_like(dx.float()))
+    assert rel_err(dxb.float()[sure], want[sure]) < 6e-3
+    assert float(((dxb.float() != 0) == kept)[sure].float().mean()) > 0.9999
+    assert rel_err(dbias, dxb.float().sum(0)) < 1e-3
+
+
 def test_layernorm_dropout_consistency():
     rows, H = 512, 768
     x = rnd(rows, H, dtype=BF, seed=1)
@@ -314,7 +344,9 @@ def ref_attention(q, k, v, kv_len, causal, scale):
                                                      (96, 12, 54, 54, False, False), (96, 12, 54, 64, False, True),
                                                      (96, 12, 64, 54, False, False), (96, 12, 99, 99, True, True),
                                                      (288, 12, 54, 64, False, True), (288, 12, 64, 54, False, False),
-                                                     (288, 12, 64, 64, False, True)])
+                                                     (288, 12, 64, 64, False, True),
+                                                     # 7 head pairs: the bias sums leave by per-tile atomics (registers hold 6)
+                                                     (40, 14, 64, 54, False, True), (3, 13, 54, 54, True, False)])
 def test_attention_fwd_bwd(B, h, Tq, Tk, causal, ragged):
     H = h * 64
     self_attn = Tq == Tk
