@@ -238,13 +238,16 @@ constexpr int LNF_STAGES = 4;
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+// H == 256 * NCH exactly (768 for every LayerNorm of the model): no column predicates.  The per-element arithmetic runs
+// on packed fp32 pairs (fma/mul/add.rn.f32x2): the kernel is bound by issue slots at its 12 warps per SM.
 template <int NCH>
 __global__ void __launch_bounds__(LNF_WARPS * 32, 1)
 ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_branch, float* dgamma, float* dbeta,
-                    float* dbias, int rows, int H, unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep,
+                    float* dbias, int rows, unsigned long long out_seed, uint32_t out_thresh, float out_inv_keep,
                     unsigned long long br_seed, uint32_t br_thresh, float br_inv_keep, const unsigned long long* salt) {
+  constexpr int H = NCH * 256;
   extern __shared__ uint4 ln_ring[];                     // [warp][stage][x | dy][NCH * 32] 16-byte chunks
   pdl_trigger();
   __shared__ float sh[3][NCH * 256];
@@ -262,19 +265,18 @@ ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int col = (lane + 32 * c) * 8;
-        if (col < H) {
-          cp_async16(dst + lane + 32 * c, x + (size_t)row * H + col);
-          cp_async16(dst + NCH * 32 + lane + 32 * c, dy + (size_t)row * H + col);
-        }
+        cp_async16(dst + lane + 32 * c, x + (size_t)row * H + col);
+        cp_async16(dst + NCH * 32 + lane + 32 * c, dy + (size_t)row * H + col);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  float ag[NCH][8], ab[NCH][8], as[NCH][8];
+  // column sums of this lane's 8 * NCH columns over all rows of the warp: pairs (col, col + 1)
+  f32x2 ag[NCH][4], ab[NCH][4], as[NCH][4];
 #pragma unroll
   for (int c = 0; c < NCH; ++c)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ag[c][j] = ab[c][j] = as[c][j] = 0.f;
+    for (int q = 0; q < 4; ++q) ag[c][q] = ab[c][q] = as[c][q] = 0ull;
   const int row0 = blockIdx.x * LNF_WARPS + w;
 #pragma unroll
   for (int s = 0; s < LNF_STAGES - 1; ++s) issue(row0 + s * nw, s);
@@ -292,81 +294,86 @@ ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
       xr[c] = src[lane + 32 * c];
       dr[c] = src[NCH * 32 + lane + 32 * c];
     }
-    uint32_t keep = 0xFFFFFFFFu;                         // dropout of the forward output (embedding LayerNorm): bit per element
-    float s1 = 0.f, s2 = 0.f;
+    const f32x2 rs2 = splat2(rs), nmurs2 = splat2(-mu * rs);
+    f32x2 s1v = 0ull, s2v = 0ull;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col = (lane + 32 * c) * 8;
-      if (col < H) {
-        float xh[8], d[8], gm[8];
-        unpack_bf16x2(xr[c].x, xh[0], xh[1]); unpack_bf16x2(xr[c].y, xh[2], xh[3]);
-        unpack_bf16x2(xr[c].z, xh[4], xh[5]); unpack_bf16x2(xr[c].w, xh[6], xh[7]);
-        unpack_bf16x2(dr[c].x, d[0], d[1]); unpack_bf16x2(dr[c].y, d[2], d[3]);
-        unpack_bf16x2(dr[c].z, d[4], d[5]); unpack_bf16x2(dr[c].w, d[6], d[7]);
-        load8f(gamma + col, gm);
-        if (out_thresh) {  // forward applied dropout after the affine: dy_affine = dy * mask / keep
+      const uint32_t xw[4] = {xr[c].x, xr[c].y, xr[c].z, xr[c].w};
+      uint32_t dw[4] = {dr[c].x, dr[c].y, dr[c].z, dr[c].w};
+      const ulonglong2 g01 = *reinterpret_cast<const ulonglong2*>(gamma + col);
+      const ulonglong2 g23 = *reinterpret_cast<const ulonglong2*>(gamma + col + 4);
+      const f32x2 gm[4] = {g01.x, g01.y, g23.x, g23.y};
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            const uint32_t hb = drop_bits2(out_key, (uint32_t)row * H + col + j);
-            const bool k0 = (hb & 0xFFFFu) >= out_thresh, k1 = (hb >> 16) >= out_thresh;
-            if (!k0) keep &= ~(1u << (8 * c + j));
-            if (!k1) keep &= ~(1u << (8 * c + j + 1));
-            d[j] = k0 ? d[j] * out_inv_keep : 0.f;
-            d[j + 1] = k1 ? d[j + 1] * out_inv_keep : 0.f;
-          }
+      for (int q = 0; q < 4; ++q) {
+        f32x2 d = bf16x2_to_f32x2(dw[q]);
+        if (out_thresh) {   // forward applied dropout after the affine (embedding LayerNorm): dy_affine = dy * mask / keep
+          const uint32_t hb = drop_bits2(out_key, (uint32_t)row * H + col + 2 * q);
+          d = mul2(d, pk2((hb & 0xFFFFu) >= out_thresh ? out_inv_keep : 0.f, (hb >> 16) >= out_thresh ? out_inv_keep : 0.f));
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xn = (xh[j] - mu) * rs;
-          const float g = d[j] * gm[j];
-          s1 += g;
-          s2 += g * xn;
-          ag[c][j] += d[j] * xn;
-          ab[c][j] += d[j];
-        }
+        const f32x2 xn = fma2(bf16x2_to_f32x2(xw[q]), rs2, nmurs2);
+        const f32x2 g = mul2(d, gm[q]);
+        s1v = add2(s1v, g);
+        s2v = fma2(g, xn, s2v);
+        ag[c][q] = fma2(d, xn, ag[c][q]);
+        ab[c][q] = add2(ab[c][q], d);
       }
     }
-    s1 = warp_sum(s1) / H;
-    s2 = warp_sum(s2) / H;
+    float s1a, s1b, s2a, s2b;
+    upk2(s1v, s1a, s1b);
+    upk2(s2v, s2a, s2b);
+    const float s1 = warp_sum(s1a + s1b) * (1.f / H), s2 = warp_sum(s2a + s2b) * (1.f / H);
+    const f32x2 ns2 = splat2(-s2), nb = splat2(-s1 * rs);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col = (lane + 32 * c) * 8;
-      if (col < H) {
-        float xh[8], d[8], gm[8], o[8];
-        unpack_bf16x2(xr[c].x, xh[0], xh[1]); unpack_bf16x2(xr[c].y, xh[2], xh[3]);
-        unpack_bf16x2(xr[c].z, xh[4], xh[5]); unpack_bf16x2(xr[c].w, xh[6], xh[7]);
-        unpack_bf16x2(dr[c].x, d[0], d[1]); unpack_bf16x2(dr[c].y, d[2], d[3]);
-        unpack_bf16x2(dr[c].z, d[4], d[5]); unpack_bf16x2(dr[c].w, d[6], d[7]);
-        load8f(gamma + col, gm);
+      const uint32_t xw[4] = {xr[c].x, xr[c].y, xr[c].z, xr[c].w};
+      const uint32_t dw[4] = {dr[c].x, dr[c].y, dr[c].z, dr[c].w};
+      const ulonglong2 g01 = *reinterpret_cast<const ulonglong2*>(gamma + col);
+      const ulonglong2 g23 = *reinterpret_cast<const ulonglong2*>(gamma + col + 4);
+      const f32x2 gm[4] = {g01.x, g01.y, g23.x, g23.y};
+      f32x2 o[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float dj = out_thresh ? (((keep >> (8 * c + j)) & 1u) ? d[j] * out_inv_keep : 0.f) : d[j];
-          o[j] = rs * (dj * gm[j] - s1 - (xh[j] - mu) * rs * s2);
+      for (int q = 0; q < 4; ++q) {
+        f32x2 d = bf16x2_to_f32x2(dw[q]);
+        if (out_thresh) {
+          const uint32_t hb = drop_bits2(out_key, (uint32_t)row * H + col + 2 * q);
+          d = mul2(d, pk2((hb & 0xFFFFu) >= out_thresh ? out_inv_keep : 0.f, (hb >> 16) >= out_thresh ? out_inv_keep : 0.f));
         }
-        store8(dx + (size_t)row * H + col, o);
-        if (dx_branch) {
+        const f32x2 xn = fma2(bf16x2_to_f32x2(xw[q]), rs2, nmurs2);
+        // rs * (g - s1 - xn * s2) with g = d * gamma
+        o[q] = fma2(fma2(xn, ns2, mul2(d, gm[q])), rs2, nb);
+      }
+      uint4 pk;
+      pk.x = f32x2_to_bf16x2(o[0]); pk.y = f32x2_to_bf16x2(o[1]); pk.z = f32x2_to_bf16x2(o[2]); pk.w = f32x2_to_bf16x2(o[3]);
+      *reinterpret_cast<uint4*>(dx + (size_t)row * H + col) = pk;
+      if (dx_branch) {
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) drop_pair(br_key, (uint32_t)row * H + col + j, br_thresh, br_inv_keep, o[j], o[j + 1]);
-          store8(dx_branch + (size_t)row * H + col, o);
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t hb = drop_bits2(br_key, (uint32_t)row * H + col + 2 * q);
+          o[q] = mul2(o[q], pk2((hb & 0xFFFFu) >= br_thresh ? br_inv_keep : 0.f, (hb >> 16) >= br_thresh ? br_inv_keep : 0.f));
         }
-        if (dbias != nullptr) {
-          // the bias gradient of the dense is the column sum of the STORED (bf16) branch gradient, as autograd forms it
-#pragma unroll
-          for (int j = 0; j < 8; ++j) as[c][j] += bf2f(f2bf(o[j]));
-        }
+        pk.x = f32x2_to_bf16x2(o[0]); pk.y = f32x2_to_bf16x2(o[1]); pk.z = f32x2_to_bf16x2(o[2]); pk.w = f32x2_to_bf16x2(o[3]);
+        *reinterpret_cast<uint4*>(dx_branch + (size_t)row * H + col) = pk;
+      }
+      if (dbias != nullptr) {
+        // the bias gradient of the dense is the column sum of the STORED (bf16) branch gradient, as autograd forms it
+        as[c][0] = add2(as[c][0], bf16x2_to_f32x2(pk.x)); as[c][1] = add2(as[c][1], bf16x2_to_f32x2(pk.y));
+        as[c][2] = add2(as[c][2], bf16x2_to_f32x2(pk.z)); as[c][3] = add2(as[c][3], bf16x2_to_f32x2(pk.w));
       }
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  // fold the CTA's warps: element (c, j) of a lane lives at [j][lane + 32 c] so a warp's adds hit 32 different banks
+  // fold the CTA's warps: element j of chunk c of a lane lives at [j][lane + 32 c] so a warp's adds hit 32 different banks
 #pragma unroll
   for (int c = 0; c < NCH; ++c)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int idx = j * (NCH * 32) + lane + 32 * c;
-      atomicAdd(&sh[0][idx], ag[c][j]);
-      atomicAdd(&sh[1][idx], ab[c][j]);
-      if (dbias != nullptr) atomicAdd(&sh[2][idx], as[c][j]);
+    for (int q = 0; q < 4; ++q) {
+      const int idx = (2 * q) * (NCH * 32) + lane + 32 * c;
+      float lo, hi;
+      upk2(ag[c][q], lo, hi); atomicAdd(&sh[0][idx], lo); atomicAdd(&sh[0][idx + NCH * 32], hi);
+      upk2(ab[c][q], lo, hi); atomicAdd(&sh[1][idx], lo); atomicAdd(&sh[1][idx + NCH * 32], hi);
+      if (dbias != nullptr) { upk2(as[c][q], lo, hi); atomicAdd(&sh[2][idx], lo); atomicAdd(&sh[2][idx + NCH * 32], hi); }
     }
   __syncthreads();
   for (int col = threadIdx.x; col < H; col += LNF_WARPS * 32) {
@@ -420,7 +427,7 @@ extern "C" int spmm_layernorm_bwd(const void* dy, const void* x, const float* me
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t le = cudaSuccess;
   static const int split = [] { const char* e = getenv("SPMM_LN_BWD_SPLIT"); return e && e[0] == '1' ? 1 : 0; }();
-  if (!split && nch <= 3 && (dgamma || dbeta || dbias)) {
+  if (!split && nch <= 3 && H == nch * 256 && (dgamma || dbeta || dbias)) {
     int ctas = (rows + LNF_WARPS - 1) / LNF_WARPS;
     if (ctas > kNumSMs) ctas = kNumSMs;
     static bool configured[4] = {false, false, false, false};
@@ -434,7 +441,7 @@ extern "C" int spmm_layernorm_bwd(const void* dy, const void* x, const float* me
     if (le == cudaSuccess)                                                                                               \
       le = launch_pdl(ln_bwd_fused_kernel<N>, dim3(ctas), dim3(LNF_WARPS * 32), ring_bytes, st,                          \
                       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx,          \
-                      (__nv_bfloat16*)dx_branch, dgamma, dbeta, dbias, rows, H, out_seed, oth, oik, branch_seed, bth,    \
+                      (__nv_bfloat16*)dx_branch, dgamma, dbeta, dbias, rows, out_seed, oth, oik, branch_seed, bth,       \
                       bik, spmm_g_rng_salt);                                                                             \
   } while (0)
     if (nch == 1) SPMM_LN_BWDF(1); else if (nch == 2) SPMM_LN_BWDF(2); else SPMM_LN_BWDF(3);
