@@ -90,6 +90,92 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
   }
 }
 
+// H == 256 * NCH (768 everywhere in the model): persistent form - a warp walks rows (stride = warps in the grid) with
+// the next row's three 16-byte loads already in flight, gamma / beta of its columns live in registers, arithmetic on
+// packed fp32 pairs.  The one-row-per-warp kernel above needed 3.5 waves for the 24576-row calls of the batched
+// passes and spent 421 instructions per row.
+constexpr int LNP_WARPS = 8;
+template <int NCH>
+__global__ void __launch_bounds__(LNP_WARPS * 32, 2)
+ln_fwd_rows_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
+                   float eps, unsigned long long seed, uint32_t thresh16, float inv_keep, const unsigned long long* salt) {
+  constexpr int H = NCH * 256;
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t key = thresh16 ? fold_seed(salted(seed, salt)) : 0u;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nw = gridDim.x * LNP_WARPS;
+  f32x2 g2[NCH][4], b2[NCH][4];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = (lane + 32 * c) * 8;
+    const ulonglong2 g01 = *reinterpret_cast<const ulonglong2*>(gamma + col), g23 = *reinterpret_cast<const ulonglong2*>(gamma + col + 4);
+    const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(beta + col), b23 = *reinterpret_cast<const ulonglong2*>(beta + col + 4);
+    g2[c][0] = g01.x; g2[c][1] = g01.y; g2[c][2] = g23.x; g2[c][3] = g23.y;
+    b2[c][0] = b01.x; b2[c][1] = b01.y; b2[c][2] = b23.x; b2[c][3] = b23.y;
+  }
+  int row = blockIdx.x * LNP_WARPS + w;
+  uint4 cur[NCH], nxt[NCH];
+  if (row < rows) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) cur[c] = *reinterpret_cast<const uint4*>(x + (size_t)row * H + (lane + 32 * c) * 8);
+  }
+  for (; row < rows; row += nw) {
+    const int nrow = row + nw;
+    if (nrow < rows) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) nxt[c] = *reinterpret_cast<const uint4*>(x + (size_t)nrow * H + (lane + 32 * c) * 8);
+    }
+    f32x2 v[NCH][4];
+    f32x2 sum2 = 0ull;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      v[c][0] = bf16x2_to_f32x2(cur[c].x); v[c][1] = bf16x2_to_f32x2(cur[c].y);
+      v[c][2] = bf16x2_to_f32x2(cur[c].z); v[c][3] = bf16x2_to_f32x2(cur[c].w);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sum2 = add2(sum2, v[c][q]);
+    }
+    float lo, hi;
+    upk2(sum2, lo, hi);
+    const float mean = warp_sum(lo + hi) * (1.f / H);
+    const f32x2 nmean2 = splat2(-mean);
+    f32x2 sq2 = 0ull;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[c][q] = add2(v[c][q], nmean2);
+        sq2 = fma2(v[c][q], v[c][q], sq2);
+      }
+    upk2(sq2, lo, hi);
+    const float rstd = rsqrtf(warp_sum(lo + hi) * (1.f / H) + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    const f32x2 rstd2 = splat2(rstd);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (lane + 32 * c) * 8;
+      f32x2 o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        o[q] = fma2(mul2(v[c][q], rstd2), g2[c][q], b2[c][q]);
+        if (thresh16) {
+          const uint32_t hb = drop_bits2(key, (uint32_t)row * H + col + 2 * q);
+          o[q] = mul2(o[q], pk2((hb & 0xFFFFu) >= thresh16 ? inv_keep : 0.f, (hb >> 16) >= thresh16 ? inv_keep : 0.f));
+        }
+      }
+      uint4 pk;
+      pk.x = f32x2_to_bf16x2(o[0]); pk.y = f32x2_to_bf16x2(o[1]); pk.z = f32x2_to_bf16x2(o[2]); pk.w = f32x2_to_bf16x2(o[3]);
+      *reinterpret_cast<uint4*>(y + (size_t)row * H + col) = pk;
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) cur[c] = nxt[c];
+  }
+}
+
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma; optionally dx_branch = dx * dropout mask.
 template <int NCH>
 __global__ void __launch_bounds__(LN_WARPS * 32)
@@ -404,6 +490,14 @@ extern "C" int spmm_layernorm_fwd(const void* x, const float* gamma, const float
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t le = cudaSuccess;
 #define SPMM_LN_FWD(N) le = launch_pdl(ln_fwd_kernel<N>, dim3(grid), dim3(LN_WARPS * 32), 0, st, (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, H, eps, seed, th, ik, spmm_g_rng_salt)
+  static const int one_row = [] { const char* e = getenv("SPMM_LN_FWD_ONE_ROW"); return e && e[0] == '1' ? 1 : 0; }();
+  if (!one_row && nch <= 3 && H == nch * 256 && rows >= 2 * kNumSMs * LNP_WARPS) {
+    const int ctas = 2 * kNumSMs;
+#define SPMM_LN_FWDP(N) le = launch_pdl(ln_fwd_rows_kernel<N>, dim3(ctas), dim3(LNP_WARPS * 32), 0, st, (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, eps, seed, th, ik, spmm_g_rng_salt)
+    if (nch == 1) SPMM_LN_FWDP(1); else if (nch == 2) SPMM_LN_FWDP(2); else SPMM_LN_FWDP(3);
+#undef SPMM_LN_FWDP
+    return le != cudaSuccess ? (int)le : 0;
+  }
   if (nch == 1) SPMM_LN_FWD(1); else if (nch == 2) SPMM_LN_FWD(2); else if (nch == 3) SPMM_LN_FWD(3); else SPMM_LN_FWD(4);
 #undef SPMM_LN_FWD
   if (le != cudaSuccess) return (int)le;
