@@ -121,7 +121,7 @@ int spmm_dgelu_bf16(const void* d_act, const void* pre_act, void* d_pre, int64_t
 int spmm_gather_rows_bf16(const void* src, const int* idx, void* dst, int n_idx, int64_t row_elems, void* stream);
 int spmm_scatter_add_rows_bf16(void* dst, const int* idx, const void* src, int n_idx, int64_t row_elems, void* stream);
 /* dst[t] = sum of src[r] over r with idx[r] == t, t < n_dst (fp32 accumulation in ascending r, written once; rows no r
- * maps to become zero); n_idx <= 1024.  Autograd of the gathers / shared K/V of SPMM_models.py:165-198. */
+ * maps to become zero); n_idx <= 4096.  Autograd of the gathers / shared K/V of SPMM_models.py:165-198. */
 int spmm_segment_sum_rows_bf16(void* dst, int n_dst, const int* idx, const void* src, int n_idx, int64_t row_elems,
                                void* stream);
 

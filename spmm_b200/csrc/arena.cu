@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(uint4* __restrict
 
 // dst[t] = sum over r with idx[r] == t of src[r] (fp32 accumulation, fixed order, written once; zero when no r maps to
 // t).  gridDim.x = destination rows, gridDim.y = column slices of a row.
-constexpr int kSegMax = 1024;
+constexpr int kSegMax = 4096;
 __global__ void __launch_bounds__(256) segment_sum_rows_kernel(uint4* __restrict__ dst, const int* __restrict__ idx,
                                                                const uint4* __restrict__ src, int n_idx,
                                                                int64_t row_vec) {
