@@ -34,7 +34,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 CFG = os.path.join(REPO, "spmm_b200", "configs")
 H, I, E, P_TOK, V = 768, 3072, 256, 54, 300
-GEMM_DRAM_BYTES_PER_LAUNCH = 105.33e6   # profiles/r2_launches_dram.csv.gz: 104 697 MB over the 994 gemm2 launches of two eager steps (ncu, cold caches)
+GEMM_DRAM_BYTES_PER_LAUNCH = 105.24e6   # profiles/r2_launches_dram.csv.gz: 104 607 MB over the 994 gemm2 launches of two eager steps (ncu, cold caches)
 
 
 def flops_per_molecule(l, B, Q):
