@@ -119,7 +119,6 @@ int spmm_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int spmm_add_bf16(void* dst, const void* src, int64_t n, void* stream); /* dst += src */
 int spmm_dgelu_bf16(const void* d_act, const void* pre_act, void* d_pre, int64_t n, void* stream); /* d_pre = d_act * gelu'(pre) */
 int spmm_gather_rows_bf16(const void* src, const int* idx, void* dst, int n_idx, int64_t row_elems, void* stream);
-int spmm_scatter_add_rows_bf16(void* dst, const int* idx, const void* src, int n_idx, int64_t row_elems, void* stream);
 /* dst[t] = sum of src[r] over r with idx[r] == t, t < n_dst (fp32 accumulation in ascending r, written once; rows no r
  * maps to become zero); n_idx <= 4096.  Autograd of the gathers / shared K/V of SPMM_models.py:165-198. */
 int spmm_segment_sum_rows_bf16(void* dst, int n_dst, const int* idx, const void* src, int n_idx, int64_t row_elems,

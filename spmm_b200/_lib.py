@@ -45,7 +45,6 @@ SIGNATURES = {
     "spmm_add_bf16": (i32, [vp, vp, i64, vp]),
     "spmm_dgelu_bf16": (i32, [vp, vp, vp, i64, vp]),
     "spmm_gather_rows_bf16": (i32, [vp, vp, vp, i32, i64, vp]),
-    "spmm_scatter_add_rows_bf16": (i32, [vp, vp, vp, i32, i64, vp]),
     "spmm_segment_sum_rows_bf16": (i32, [vp, i32, vp, vp, i32, i64, vp]),
     "spmm_itc_fwd_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, f32, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                i64, vp]),

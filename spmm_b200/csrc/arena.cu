@@ -173,30 +173,6 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint4* __restric
   for (int64_t i = threadIdx.x; i < row_vec; i += blockDim.x) d[i] = s[i];
 }
 
-// dst[idx[r]] += src[r]; duplicates in idx are legal (hard negatives may repeat) -> one CTA per DESTINATION row
-__global__ void __launch_bounds__(256) scatter_add_rows_kernel(uint4* __restrict__ dst, const int* __restrict__ idx,
-                                                               const uint4* __restrict__ src, int n_idx,
-                                                               int64_t row_vec) {
-  const int target = blockIdx.x;
-  // gridDim.y CTAs share a destination row (column slices): 96 CTAs of 98 KB rows left most SMs idle
-  const int64_t per = (row_vec + gridDim.y - 1) / gridDim.y;
-  const int64_t i0 = blockIdx.y * per, i1 = i0 + per < row_vec ? i0 + per : row_vec;
-  for (int r = 0; r < n_idx; ++r) {
-    if (idx[r] != target) continue;
-    const uint4* s = src + (int64_t)r * row_vec;
-    uint4* d = dst + (int64_t)target * row_vec;
-    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-      uint4 a = d[i];
-      const uint4 b = s[i];
-      float x0, x1, y0, y1;
-#define SPMM_ADD2(c) unpack_bf16x2(a.c, x0, x1); unpack_bf16x2(b.c, y0, y1); a.c = pack_bf16x2(x0 + y0, x1 + y1);
-      SPMM_ADD2(x) SPMM_ADD2(y) SPMM_ADD2(z) SPMM_ADD2(w)
-#undef SPMM_ADD2
-      d[i] = a;
-    }
-  }
-}
-
 // dst[t] = sum over r with idx[r] == t of src[r] (fp32 accumulation, fixed order, written once; zero when no r maps to
 // t).  gridDim.x = destination rows, gridDim.y = column slices of a row.
 constexpr int kSegMax = 4096;
@@ -390,12 +366,3 @@ extern "C" int spmm_segment_sum_rows_bf16(void* dst, int n_dst, const int* idx, 
   return 0;
 }
 
-extern "C" int spmm_scatter_add_rows_bf16(void* dst, const int* idx, const void* src, int n_idx, int64_t row_elems,
-                                          void* stream) {
-  SPMM_ARG(src && idx && dst && n_idx > 0 && row_elems % 8 == 0 && (((uintptr_t)dst | (uintptr_t)src) & 15) == 0);
-  // destination rows are indexed 0..n_idx-1 (the in-batch gather of SPMM_models.py:165-178 is a map batch -> batch)
-  scatter_add_rows_kernel<<<dim3(n_idx, row_elems >= 8192 ? 8 : 1), 256, 0, (cudaStream_t)stream>>>(
-      (uint4*)dst, idx, (const uint4*)src, n_idx, row_elems / 8);
-  SPMM_CHECK_LAUNCH();
-  return 0;
-}

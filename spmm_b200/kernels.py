@@ -134,10 +134,6 @@ def gather_rows(src, idx, n_idx):
     return out
 
 
-def scatter_add_rows(dst, idx, src):
-    call("spmm_scatter_add_rows_bf16", dst.data_ptr(), idx.data_ptr(), src.data_ptr(), src.shape[0], src[0].numel(), _st())
-
-
 def segment_sum_rows(src, idx, n_dst):
     """out[t] = sum of src[r] over idx[r] == t; src [n_idx, ...] bf16, idx int32 on the device."""
     out = torch.empty((n_dst,) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)

@@ -58,7 +58,7 @@ def test_adamw_matches_torch():
     assert torch.equal(p, before)
 
 
-def test_colsum_gather_scatter_add():
+def test_colsum_gather_segment_sum():
     x = rnd(1000, 768, dtype=BF)
     out = torch.zeros(768, device=DEV)
     K.colsum(x, out)
@@ -67,10 +67,7 @@ def test_colsum_gather_scatter_add():
     idx = torch.tensor([3, 3, 0, 11, 7, 7, 7, 1, 2, 5, 9, 10], device=DEV, dtype=torch.int32)
     got = K.gather_rows(src, idx, 12)
     assert torch.equal(got, src[idx.long()])
-    dst = torch.zeros_like(src)
-    K.scatter_add_rows(dst, idx, src)
     ref = torch.zeros(12, 54, 128, device=DEV).index_add_(0, idx.long(), src.float())
-    assert rel_err(dst, ref) < 1e-2
     assert rel_err(K.segment_sum_rows(src, idx, 12), ref) < 4e-3
     a, b = rnd(4096, dtype=BF), rnd(4096, seed=9, dtype=BF)
     assert torch.equal(K.add_(a.clone(), b), (a.float() + b.float()).to(BF))
